@@ -1,0 +1,550 @@
+// kernels.cuh -- sm_100a device code for the HnH local kernels (K1 SDDMM, K2 SpMM,
+// K3 fused SDDMM->SpMM) and the small value-plumbing / row-algebra kernels.
+//
+// What these replace (reference, CPU): StandardKernel::sddmm_local
+// (sparse_kernels.cpp:13-57, an OpenMP loop over nonzeros) and
+// StandardKernel::spmm_local (sparse_kernels.cpp:59-127, mkl_sparse_d_mm).
+//
+// Design: the path is an r-wide gather-dot, HBM-bound
+// (~0.24 flop/B in fp64); no tensor-core path.  One group of G lanes owns one CSR row:
+//   * the row-side factor row (X[row], r doubles) lives in registers for the whole row;
+//   * a chunk of G nonzeros' (col, value) is read coalesced, one per lane, and broadcast
+//     inside the group with shuffles;
+//   * each gathered Y row is read with 256-bit (LDG.E.256, sm_100) or 128-bit loads,
+//     UN rows in flight per lane;
+//   * the r-wide dot is reduced with an xor-butterfly of width G;
+//   * results of a chunk are written back coalesced (lane k owns nonzero k).
+// SpMM / fused accumulate the output row in registers in stored CSR order (bit-compatible
+// with the row-major CSR restatement in oracle/hnh_oracle.c) and touch Y[row] once.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hnh {
+
+// ------------------------------------------------------------------ vector loads --------
+// Gather loads: read-only path, normal L2 policy (gathered factor rows are the only data
+// with any reuse).  Stream loads: read-only, do not allocate in L1, evict-first in L2.
+template <int VW>
+__device__ __forceinline__ void ld_gather(double (&d)[VW], const double *p);
+template <>
+__device__ __forceinline__ void ld_gather<4>(double (&d)[4], const double *p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3])
+                 : "l"(p));
+}
+template <>
+__device__ __forceinline__ void ld_gather<2>(double (&d)[2], const double *p) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(d[0]), "=d"(d[1])
+                 : "l"(p));
+}
+template <>
+__device__ __forceinline__ void ld_gather<1>(double (&d)[1], const double *p) {
+    d[0] = __ldg(p);
+}
+
+// plain (coherent) vector load / store for read-modify-write of output rows
+template <int VW>
+__device__ __forceinline__ void ld_rw(double (&d)[VW], const double *p);
+template <>
+__device__ __forceinline__ void ld_rw<4>(double (&d)[4], const double *p) {
+    asm volatile("ld.global.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3])
+                 : "l"(p)
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void ld_rw<2>(double (&d)[2], const double *p) {
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(d[0]), "=d"(d[1])
+                 : "l"(p)
+                 : "memory");
+}
+template <int VW>
+__device__ __forceinline__ void st_rw(double *p, const double (&d)[VW]);
+template <>
+__device__ __forceinline__ void st_rw<4>(double *p, const double (&d)[4]) {
+    asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(d[0]),
+                 "d"(d[1]), "d"(d[2]), "d"(d[3])
+                 : "memory");
+}
+template <>
+__device__ __forceinline__ void st_rw<2>(double *p, const double (&d)[2]) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(d[0]), "d"(d[1])
+                 : "memory");
+}
+
+__device__ __forceinline__ int64_t ld_stream_i64(const int64_t *p) {
+    int64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask(int lane) {
+    if constexpr (G == 32) {
+        return 0xffffffffu;
+    } else {
+        return ((1u << G) - 1u) << (lane & ~(G - 1));
+    }
+}
+
+template <int G>
+__device__ __forceinline__ double group_allreduce(double d, unsigned mask) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) d += __shfl_xor_sync(mask, d, o, G);
+    return d;
+}
+
+// ------------------------------------------------------------------ K1: SDDMM ------------
+// values[j] += X[row] . Y[col_idx[j]] for every nonzero j of every CSR row.
+template <int R, int G, int VW, int UN, bool BETA0>
+__global__ void __launch_bounds__(256)
+sddmm_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                 double *__restrict__ values, int64_t rows, const double *__restrict__ X,
+                 const double *__restrict__ Y) {
+    constexpr int NV = R / (G * VW);
+    static_assert(NV * G * VW == R, "R must equal NV*G*VW");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; row < rows;
+         row += ngroups) {
+        double x[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++) ld_gather<VW>(x[v], X + row * R + (v * G + gl) * VW);
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        for (int64_t j = s; j < e; j += G) {
+            const int cnt = (e - j < G) ? (int)(e - j) : G;
+            int64_t mycol = 0;
+            if (gl < cnt) mycol = ld_stream_i64(col_idx + j + gl);
+            double mine = 0.0;
+            for (int k0 = 0; k0 < cnt; k0 += UN) {
+                double y[UN][NV][VW];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int k = k0 + u;
+                    const int64_t c = __shfl_sync(gmask, mycol, k < G ? k : G - 1, G);
+                    if (k < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+                            ld_gather<VW>(y[u][v], Y + c * R + (v * G + gl) * VW);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int w = 0; w < VW; w++) y[u][v][w] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
+                    d = group_allreduce<G>(d, gmask);
+                    if (gl == k0 + u) mine = d;
+                }
+            }
+            if (gl < cnt) {
+                if (BETA0) values[j + gl] = mine;
+                else values[j + gl] += mine;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K2: SpMM -------------
+// Y[row] += sum_j values[j] * X[col_idx[j]]   (row-major, alpha = beta = 1).
+template <int R, int G, int VW, int UN, bool BETA0>
+__global__ void __launch_bounds__(256)
+spmm_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                const double *__restrict__ values, int64_t rows, const double *__restrict__ X,
+                double *__restrict__ Y) {
+    constexpr int NV = R / (G * VW);
+    static_assert(NV * G * VW == R, "R must equal NV*G*VW");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; row < rows;
+         row += ngroups) {
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        if (!BETA0 && s == e) continue;  // Y[row] += 0
+        double acc[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            if (BETA0) {
+#pragma unroll
+                for (int w = 0; w < VW; w++) acc[v][w] = 0.0;
+            } else {
+                ld_rw<VW>(acc[v], Y + row * R + (v * G + gl) * VW);
+            }
+        }
+        for (int64_t j = s; j < e; j += G) {
+            const int cnt = (e - j < G) ? (int)(e - j) : G;
+            int64_t mycol = 0;
+            double myval = 0.0;
+            if (gl < cnt) {
+                mycol = ld_stream_i64(col_idx + j + gl);
+                myval = ld_stream_f64(values + j + gl);
+            }
+            for (int k0 = 0; k0 < cnt; k0 += UN) {
+                double xg[UN][NV][VW];
+                double vv[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int k = k0 + u;
+                    const int src = k < G ? k : G - 1;
+                    const int64_t c = __shfl_sync(gmask, mycol, src, G);
+                    vv[u] = __shfl_sync(gmask, myval, src, G);
+                    if (k < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+                            ld_gather<VW>(xg[u][v], X + c * R + (v * G + gl) * VW);
+                    } else {
+                        vv[u] = 0.0;
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int w = 0; w < VW; w++) xg[u][v][w] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++)
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++)
+                            acc[v][w] = fma(vv[u], xg[u][v][w], acc[v][w]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) st_rw<VW>(Y + row * R + (v * G + gl) * VW, acc[v]);
+    }
+}
+
+// ------------------------------------------------------------------ K3: fused ------------
+// values[j] += X[row].Y[col_j];  Out[row] += sum_j values[j] * Y[col_j]; one gather per nnz.
+// BETA0: values = dot and Out = result (no read of the old contents); Out may then alias X
+// (each row of X is read only by the group that later writes that row of Out).
+template <int R, int G, int VW, int UN, bool BETA0>
+__global__ void __launch_bounds__(256)
+fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                 double *__restrict__ values, int64_t rows, const double *X,
+                 const double *__restrict__ Y, double *Out) {
+    constexpr int NV = R / (G * VW);
+    static_assert(NV * G * VW == R, "R must equal NV*G*VW");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; row < rows;
+         row += ngroups) {
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        if (!BETA0 && s == e) continue;
+        double x[NV][VW], acc[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            ld_rw<VW>(x[v], X + row * R + (v * G + gl) * VW);
+            if (BETA0) {
+#pragma unroll
+                for (int w = 0; w < VW; w++) acc[v][w] = 0.0;
+            } else {
+                ld_rw<VW>(acc[v], Out + row * R + (v * G + gl) * VW);
+            }
+        }
+        for (int64_t j = s; j < e; j += G) {
+            const int cnt = (e - j < G) ? (int)(e - j) : G;
+            int64_t mycol = 0;
+            double myval = 0.0;
+            if (gl < cnt) {
+                mycol = ld_stream_i64(col_idx + j + gl);
+                if (!BETA0) myval = values[j + gl];
+            }
+            for (int k0 = 0; k0 < cnt; k0 += UN) {
+                double y[UN][NV][VW];
+                double vold[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int k = k0 + u;
+                    const int src = k < G ? k : G - 1;
+                    const int64_t c = __shfl_sync(gmask, mycol, src, G);
+                    vold[u] = __shfl_sync(gmask, myval, src, G);
+                    if (k < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+                            ld_gather<VW>(y[u][v], Y + c * R + (v * G + gl) * VW);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int w = 0; w < VW; w++) y[u][v][w] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
+                    d = group_allreduce<G>(d, gmask);
+                    const double vnew = vold[u] + d;
+                    if (gl == k0 + u) myval = vnew;
+                    if (k0 + u < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int w = 0; w < VW; w++)
+                                acc[v][w] = fma(vnew, y[u][v][w], acc[v][w]);
+                    }
+                }
+            }
+            if (gl < cnt) values[j + gl] = myval;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++) st_rw<VW>(Out + row * R + (v * G + gl) * VW, acc[v]);
+    }
+}
+
+// ------------------------------------------------------------------ COO-driven SDDMM -----
+// The reference's literal formulation: per nonzero i, rows from row_idx[i]
+// (sparse_kernels.cpp:45-47).  G lanes per nonzero, chunks of G nonzeros per group.
+template <int R, int G, int VW, int UN>
+__global__ void __launch_bounds__(256)
+sddmm_coo_kernel(const int64_t *__restrict__ row_idx, const int64_t *__restrict__ col_idx,
+                 double *__restrict__ values, int64_t nnz, const double *__restrict__ X,
+                 const double *__restrict__ Y) {
+    constexpr int NV = R / (G * VW);
+    static_assert(NV * G * VW == R, "R must equal NV*G*VW");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    const int64_t nchunks = (nnz + G - 1) / G;
+    for (int64_t ch = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; ch < nchunks;
+         ch += ngroups) {
+        const int64_t j = ch * G;
+        const int cnt = (nnz - j < G) ? (int)(nnz - j) : G;
+        int64_t mycol = 0, myrow = 0;
+        if (gl < cnt) {
+            mycol = ld_stream_i64(col_idx + j + gl);
+            myrow = ld_stream_i64(row_idx + j + gl);
+        }
+        double mine = 0.0;
+        for (int k0 = 0; k0 < cnt; k0 += UN) {
+            double y[UN][NV][VW], x[UN][NV][VW];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int k = k0 + u;
+                const int src = k < G ? k : G - 1;
+                const int64_t c = __shfl_sync(gmask, mycol, src, G);
+                const int64_t rr = __shfl_sync(gmask, myrow, src, G);
+                if (k < cnt) {
+#pragma unroll
+                    for (int v = 0; v < NV; v++) {
+                        ld_gather<VW>(y[u][v], Y + c * R + (v * G + gl) * VW);
+                        ld_gather<VW>(x[u][v], X + rr * R + (v * G + gl) * VW);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) y[u][v][w] = x[u][v][w] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                double d = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+#pragma unroll
+                    for (int w = 0; w < VW; w++) d = fma(x[u][v][w], y[u][v][w], d);
+                d = group_allreduce<G>(d, gmask);
+                if (gl == k0 + u) mine = d;
+            }
+        }
+        if (gl < cnt) values[j + gl] += mine;
+    }
+}
+
+// ------------------------------------------------------------------ any-r kernels --------
+// Warp per row, scalar strided loads; correct for every r >= 1 and any alignment.
+__global__ void __launch_bounds__(256)
+sddmm_generic_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                     double *__restrict__ values, int64_t rows, const double *__restrict__ X,
+                     const double *__restrict__ Y, int r) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += nwarps) {
+        const int64_t s = rowStart[row], e = rowStart[row + 1];
+        const double *xr = X + row * (int64_t)r;
+        for (int64_t j = s; j < e; j++) {
+            const double *yr = Y + col_idx[j] * (int64_t)r;
+            double d = 0.0;
+            for (int k = lane; k < r; k += 32) d = fma(xr[k], yr[k], d);
+            d = group_allreduce<32>(d, 0xffffffffu);
+            if (lane == 0) values[j] += d;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sddmm_coo_generic_kernel(const int64_t *__restrict__ row_idx,
+                         const int64_t *__restrict__ col_idx, double *__restrict__ values,
+                         int64_t nnz, const double *__restrict__ X,
+                         const double *__restrict__ Y, int r) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nnz;
+         j += nwarps) {
+        const double *xr = X + row_idx[j] * (int64_t)r;
+        const double *yr = Y + col_idx[j] * (int64_t)r;
+        double d = 0.0;
+        for (int k = lane; k < r; k += 32) d = fma(xr[k], yr[k], d);
+        d = group_allreduce<32>(d, 0xffffffffu);
+        if (lane == 0) values[j] += d;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+spmm_generic_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                    const double *__restrict__ values, int64_t rows,
+                    const double *__restrict__ X, double *__restrict__ Y, int r) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += nwarps) {
+        const int64_t s = rowStart[row], e = rowStart[row + 1];
+        if (s == e) continue;
+        for (int k = lane; k < r; k += 32) {
+            double acc = Y[row * (int64_t)r + k];
+            for (int64_t j = s; j < e; j++)
+                acc = fma(values[j], X[col_idx[j] * (int64_t)r + k], acc);
+            Y[row * (int64_t)r + k] = acc;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+fused_generic_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                     double *values, int64_t rows, const double *__restrict__ X,
+                     const double *__restrict__ Y, double *__restrict__ Out, int r) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += nwarps) {
+        const int64_t s = rowStart[row], e = rowStart[row + 1];
+        if (s == e) continue;
+        const double *xr = X + row * (int64_t)r;
+        for (int64_t j = s; j < e; j++) {
+            const double *yr = Y + col_idx[j] * (int64_t)r;
+            double d = 0.0;
+            for (int k = lane; k < r; k += 32) d = fma(xr[k], yr[k], d);
+            d = group_allreduce<32>(d, 0xffffffffu);
+            if (lane == 0) values[j] += d;
+        }
+        __syncwarp();
+        for (int k = lane; k < r; k += 32) {
+            double acc = Out[row * (int64_t)r + k];
+            for (int64_t j = s; j < e; j++)
+                acc = fma(values[j], Y[col_idx[j] * (int64_t)r + k], acc);
+            Out[row * (int64_t)r + k] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K4 + row algebra -----
+__global__ void fill_kernel(double *__restrict__ dst, int64_t n, double value) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = value;
+}
+
+__global__ void hadamard_kernel(double *__restrict__ dst, const double *__restrict__ a,
+                                const double *__restrict__ b, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = a[i] * b[i];
+}
+
+__global__ void expand_row_idx_kernel(const int64_t *__restrict__ rowStart, int64_t rows,
+                                      int64_t *__restrict__ row_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += nwarps) {
+        const int64_t s = rowStart[row], e = rowStart[row + 1];
+        for (int64_t j = s + lane; j < e; j += 32) row_idx[j] = row;
+    }
+}
+
+__global__ void batch_dot_kernel(double *__restrict__ out, const double *__restrict__ A,
+                                 const double *__restrict__ B, int64_t rows, int r) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows;
+         row += nwarps) {
+        double d = 0.0;
+        for (int k = lane; k < r; k += 32)
+            d = fma(A[row * (int64_t)r + k], B[row * (int64_t)r + k], d);
+        d = group_allreduce<32>(d, 0xffffffffu);
+        if (lane == 0) out[row] = d;
+    }
+}
+
+__global__ void row_axpy_kernel(double *D, const double *C, double alpha,
+                                const double *__restrict__ s, const double *M, int64_t rows,
+                                int r) {
+    const int64_t n = rows * (int64_t)r;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double sc = s ? s[i / r] : 1.0;
+        D[i] = C[i] + alpha * sc * M[i];
+    }
+}
+
+__global__ void vec_quotient_kernel(double *out, const double *a, double ca, const double *b,
+                                    double cb, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = (a[i] + ca) / (b[i] + cb);
+}
+
+__global__ void axpby_kernel(double *dst, double alpha, const double *x, double beta,
+                             const double *y, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = alpha * x[i] + (y ? beta * y[i] : 0.0);
+}
+
+__global__ void squared_norm_kernel(double *out, const double *__restrict__ x, int64_t n) {
+    __shared__ double warp_sums[8];
+    double acc = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        acc = fma(x[i], x[i], acc);
+    acc = group_allreduce<32>(acc, 0xffffffffu);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_sums[w];
+        atomicAdd(out, t);
+    }
+}
+
+}  // namespace hnh

@@ -1,0 +1,154 @@
+/*
+ * hnh_b200.h -- C ABI of the B200-native local kernels (libhnh_b200.so).
+ *
+ * This is the drop-in boundary under the reference's C++ plugin interface
+ * `KernelImplementation` (reference sparse_kernels.h:15-79).  Every entry point is
+ * `extern "C"`, takes plain pointers and sizes (no torch / Eigen / MKL types), enqueues
+ * its work on the CUDA stream passed as `void *stream` (NULL = legacy default stream) and
+ * returns 0 on success or a negative HNH_E_* code -- it never prints-and-exits the way the
+ * reference does (sparse_kernels.cpp:75-83).  `hnh_last_error_string()` describes the last
+ * failure on the calling thread.
+ *
+ * Unless a name ends in `_host`, all data pointers are DEVICE pointers.
+ * Dense operands are row-major, contiguous, leading dimension = r (reference common.h:13,
+ * `DenseMatrix`), fp64.  Index arrays are int64 (MKL_INT under -DMKL_ILP64, reference
+ * CMakeLists.txt:37).  CSR arrays are the four vectors of the reference's `CSRHandle`
+ * (SpmatLocal.hpp:55-62): values, col_idx, rowStart (rows+1 entries), row_idx (expanded).
+ *
+ * There is no CPU fallback behind this ABI: without a CUDA device every compute entry
+ * point fails with HNH_E_CUDA.
+ */
+#ifndef HNH_B200_H
+#define HNH_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HNH_OK 0
+#define HNH_E_INVALID (-1) /* bad argument (null pointer, negative size, r <= 0 ...)     */
+#define HNH_E_CUDA (-2)    /* a CUDA runtime call or kernel launch failed                */
+#define HNH_E_MODE (-3)    /* block transposition does not match the requested SpMM mode */
+#define HNH_E_ALLOC (-4)   /* device or pinned-host allocation failed                    */
+#define HNH_E_COMM (-5)    /* NCCL / transport failure                                   */
+
+/* flags (bit set) */
+#define HNH_FLAG_DEFAULT 0
+#define HNH_FLAG_FORCE_GENERIC 1 /* use the any-r scalar kernel (testing)                  */
+#define HNH_FLAG_FORCE_DIRECT 2  /* use the direct-load row kernels instead of TMA-staged */
+/* BETA0: overwrite instead of accumulate -- sddmm: values = dot; spmm: Y = CSR*X;
+ * fused: values = dot, Out = result (Out may then alias X).  Equivalent to zeroing the
+ * output first (setValuesConstant(0) / setZero(), SpmatLocal.hpp:595-605,
+ * distributed_sparse.h:275) but without the extra pass over memory. */
+#define HNH_FLAG_BETA0 4
+
+/* ABI / build identification. */
+int hnh_abi_version(void);
+const char *hnh_build_info(void);
+const char *hnh_last_error_string(void);
+/* Number of kernel launches issued through this library by the calling process so far
+ * (bench.py reports the delta over its timed region as `gpu_launches`). */
+uint64_t hnh_launch_count(void);
+
+/* ---- K1: SDDMM -- replaces StandardKernel::sddmm_local (sparse_kernels.cpp:13-57) ------
+ * values[i] += sum_k X[row(i), k] * Y[col_idx[i], k]   for every nonzero i of the block.
+ * (X, Y) are already role-resolved: (A, B) for a non-transposed block, (B, A) for a
+ * transposed one (sparse_kernels.cpp:29-38).  `rows` = number of CSR rows of the block,
+ * rowStart[rows] == nnz.  Accumulates (+=), exactly like the reference; callers zero
+ * `values` first (SpmatLocal::setValuesConstant, SpmatLocal.hpp:595-605).
+ * nnz == 0 or rows == 0 is a successful no-op (sparse_kernels.cpp:25-27). */
+int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *values,
+                  int64_t rows, int64_t nnz, const double *X, const double *Y, int r,
+                  int flags, void *stream);
+
+/* Same operation driven by the expanded COO arrays the reference kernel actually reads
+ * (`row_idx[i]`, `col_idx[i]`, sparse_kernels.cpp:45-47); needs no rowStart. */
+int hnh_sddmm_coo_f64(const int64_t *row_idx, const int64_t *col_idx, double *values,
+                      int64_t nnz, const double *X, const double *Y, int r, int flags,
+                      void *stream);
+
+/* ---- K2: SpMM -- replaces StandardKernel::spmm_local (sparse_kernels.cpp:59-127) -------
+ * Y[rows x r] += CSR[rows x *] * X   (alpha = beta = 1, row-major, ld = r: the
+ * mkl_sparse_d_mm call at sparse_kernels.cpp:95-120).  X is gathered by col_idx.  The
+ * kernel never bounds-checks col_idx against a column count (the reference declares too few
+ * columns in 15D_sparse_shift.hpp:132). */
+int hnh_spmm_f64(const int64_t *rowStart, const int64_t *col_idx, const double *values,
+                 int64_t rows, int64_t nnz, const double *X, double *Y, int r, int flags,
+                 void *stream);
+
+/* ---- K3: fused SDDMM -> SpMM on one block ------------------------------------------------
+ * Replaces the two back-to-back triple_function calls of the fusion-2 loop body
+ * (15D_dense_shift.hpp:203-217):  values[i] += X[row(i)] . Y[col(i)];  then
+ * Out[row] += sum_{i in row} values[i] * Y[col(i)]   -- with ONE gather of each Y row. */
+int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *values,
+                  int64_t rows, int64_t nnz, const double *X, const double *Y, double *Out,
+                  int r, int flags, void *stream);
+
+/* ---- K4: value plumbing (SpmatLocal.hpp:571-605, 15D_dense_shift.hpp:366) -------------- */
+int hnh_fill_f64(double *dst, int64_t n, double value, void *stream);
+/* dst[i] = a[i] * b[i]  (VectorXd::cwiseProduct of SValues and getCSRValues()) */
+int hnh_hadamard_f64(double *dst, const double *a, const double *b, int64_t n, void *stream);
+/* row_idx[i] = CSR row of nonzero i (SpmatLocal.hpp:139-147,160-163) */
+int hnh_expand_row_idx(const int64_t *rowStart, int64_t rows, int64_t nnz, int64_t *row_idx,
+                       void *stream);
+
+/* ---- dense row algebra used between fusedSpMM calls by the ALS-CG caller
+ *      (als_conjugate_gradients.cpp:9-29,99-138) ------------------------------------------ */
+/* out[i] = sum_k A[i,k] * B[i,k]   (batch_dot_product) */
+int hnh_batch_dot_f64(double *out, const double *A, const double *B, int64_t rows, int r,
+                      void *stream);
+/* D[i,k] = C[i,k] + alpha * s[i] * M[i,k]   (X += scale_matrix_rows(s, M) and friends;
+ * s may be NULL meaning all-ones; D may alias C or M) */
+int hnh_row_axpy_f64(double *D, const double *C, double alpha, const double *s,
+                     const double *M, int64_t rows, int r, void *stream);
+/* elementwise vector helpers: out = (a + ca) / (b + cb) */
+int hnh_vec_quotient_f64(double *out, const double *a, double ca, const double *b, double cb,
+                         int64_t n, void *stream);
+/* dst = alpha * x + beta * y elementwise (y may be NULL when beta == 0) */
+int hnh_axpby_f64(double *dst, double alpha, const double *x, double beta, const double *y,
+                  int64_t n, void *stream);
+/* *out (device scalar) = sum x[i]^2 */
+int hnh_squared_norm_f64(double *out, const double *x, int64_t n, void *stream);
+
+/* ---- host-side setup helpers (untimed; HOST pointers) --------------------------------------
+ * hnh_er_generate_host replaces the CombBLAS Graph500 generator call of
+ * SpmatLocal::loadTuples(false, logM, nnz_per_row) (SpmatLocal.hpp:499-516): rows
+ * [row_lo,row_hi) of the seeded N x N Erdos-Renyi matrix, sorted (row, col), unique, values 1.
+ * Returns the tuple count (>= 0) or a negative HNH_E_* code. */
+int64_t hnh_er_generate_host(int logM, int nnz_per_row, uint64_t seed, int64_t row_lo,
+                             int64_t row_hi, uint64_t *rows_out, uint64_t *cols_out,
+                             double *vals_out, int64_t capacity);
+/* hnh_coo_to_csr_host replaces the MKL inspector sequence of the CSRLocal constructor
+ * (SpmatLocal.hpp:117-147): COO -> CSR, optional transpose, stable.  rowStart has
+ * (transpose ? cols : rows) + 1 entries; row_idx (expanded stored-row index) may be NULL. */
+int hnh_coo_to_csr_host(int64_t rows, int64_t cols, int64_t nnz, const uint64_t *r,
+                        const uint64_t *c, const double *v, int transpose, int64_t *rowStart,
+                        int64_t *col_idx, int64_t *row_idx, double *values);
+
+/* ---- host-buffer entry points (pinned or pageable HOST pointers) -------------------------
+ * One call = H2D of the dense operands and values, the kernel(s), D2H of the results, all
+ * inside the call; the block's CSR structure is taken from a resident handle made once with
+ * hnh_block_create_host (the reference also builds its CSR once, SpmatLocal.hpp:78-188).
+ * These are what bench.py's `e2e` leg times. */
+typedef struct hnh_block hnh_block_t;
+int hnh_block_create_host(const int64_t *rowStart, const int64_t *col_idx, int64_t rows,
+                          int64_t cols, int64_t nnz, int r_max, hnh_block_t **out);
+void hnh_block_destroy(hnh_block_t *blk);
+/* op: 0 = sddmm (values_io += X.Y), 1 = spmm (Out += CSR*Y with values_io), 2 = fused.
+ * X: rows x r, Y: cols x r, Out: rows x r (op 1, 2), values_io: nnz.
+ * run_flags: HNH_RUN_ZERO_VALUES = start from values == 0 on the device instead of copying
+ * values_io in (SpmatLocal::setValuesConstant(0), SpmatLocal.hpp:595-605);
+ * HNH_RUN_ZERO_OUT = start from Out == 0 on the device instead of copying Out in
+ * (`localA.setZero()`, distributed_sparse.h:275,304). */
+#define HNH_RUN_ZERO_VALUES 1
+#define HNH_RUN_ZERO_OUT 2
+int hnh_block_run_host(hnh_block_t *blk, int op, const double *X, const double *Y,
+                       double *values_io, double *Out, int r, int run_flags, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HNH_B200_H */
