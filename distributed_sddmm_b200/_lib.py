@@ -29,6 +29,7 @@ ABI = {
     "hnh_spmm_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_fused_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_fill_f64": (C.c_int, [_P, _I64, C.c_double, _P]),
+    "hnh_random_uniform_f64": (C.c_int, [_P, _I64, C.c_uint64, _P]),
     "hnh_hadamard_f64": (C.c_int, [_P, _P, _P, _I64, _P]),
     "hnh_expand_row_idx": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "hnh_batch_dot_f64": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P]),
@@ -67,3 +68,82 @@ def check(rc: int, what: str = "hnh call") -> None:
     if rc != 0:
         msg = lib().hnh_last_error_string().decode()
         raise RuntimeError(f"{what} failed with code {rc}: {msg}")
+
+
+# ---- driver ABI (include/hnh_b200_driver.h) --------------------------------------------------
+class AlgDims(C.Structure):
+    _fields_ = [("M", C.c_int64), ("N", C.c_int64), ("R", C.c_int64), ("p", C.c_int), ("c", C.c_int),
+                ("localArows", C.c_int), ("localAcols", C.c_int), ("localBrows", C.c_int),
+                ("localBcols", C.c_int), ("s_values", C.c_int64), ("st_values", C.c_int64),
+                ("r_split", C.c_int), ("grid_i", C.c_int), ("grid_j", C.c_int), ("grid_k", C.c_int),
+                ("n_a_submatrices", C.c_int), ("n_b_submatrices", C.c_int)]
+
+
+_SZ = C.c_size_t
+_PSZ = C.POINTER(C.c_size_t)
+CB_SENDRECV = C.CFUNCTYPE(C.c_int, _P, C.c_int, _P, _SZ, C.c_int, _P, _SZ, C.c_int)
+CB_ALLGATHER = C.CFUNCTYPE(C.c_int, _P, C.c_int, _P, _P, _SZ)
+CB_REDUCE_SCATTER = C.CFUNCTYPE(C.c_int, _P, C.c_int, _P, _P, _SZ)
+CB_ALLREDUCE = C.CFUNCTYPE(C.c_int, _P, C.c_int, _P, _SZ)
+CB_ALLTOALLV = C.CFUNCTYPE(C.c_int, _P, C.c_int, _P, _PSZ, _PSZ, _P, _PSZ, _PSZ)
+CB_BARRIER = C.CFUNCTYPE(C.c_int, _P, C.c_int)
+CB_SPLIT = C.CFUNCTYPE(C.c_int, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                       C.POINTER(C.c_int))
+
+
+class ExternalTransport(C.Structure):
+    _fields_ = [("ctx", _P), ("sendrecv", CB_SENDRECV), ("allgather", CB_ALLGATHER),
+                ("reduce_scatter_f64", CB_REDUCE_SCATTER), ("allreduce_f64", CB_ALLREDUCE),
+                ("alltoallv", CB_ALLTOALLV), ("barrier", CB_BARRIER), ("split", CB_SPLIT)]
+
+
+_PP = C.POINTER(_P)
+ABI.update({
+    "hnhd_init_self": (C.c_int, []),
+    "hnhd_nccl_unique_id": (C.c_int, [C.c_char_p]),
+    "hnhd_init_nccl": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
+    "hnhd_init_external": (C.c_int, [C.c_int, C.c_int, C.POINTER(ExternalTransport)]),
+    "hnhd_finalize": (C.c_int, []),
+    "hnhd_world_rank": (C.c_int, []),
+    "hnhd_world_size": (C.c_int, []),
+    "hnhd_barrier": (C.c_int, []),
+    "hnhd_device_synchronize": (C.c_int, []),
+    "hnhd_spmat_load_er": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _PP]),
+    "hnhd_spmat_from_tuples": (C.c_int, [C.c_uint64, C.c_uint64, _P, _P, _P, _I64, _PP]),
+    "hnhd_spmat_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_int64)]),
+    "hnhd_spmat_tuples": (C.c_int, [_P, _P, _P, _P, _I64]),
+    "hnhd_spmat_destroy": (None, [_P]),
+    "hnhd_alg_create": (C.c_int, [C.c_char_p, _P, C.c_int, C.c_int, _PP]),
+    "hnhd_alg_destroy": (None, [_P]),
+    "hnhd_alg_dims": (C.c_int, [_P, C.POINTER(AlgDims)]),
+    "hnhd_alg_submatrices": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "hnhd_alg_info_json": (C.c_int, [_P, C.c_char_p, _SZ]),
+    "hnhd_alg_perf_json": (C.c_int, [_P, C.c_char_p, _SZ]),
+    "hnhd_alg_reset_timers": (C.c_int, [_P]),
+    "hnhd_alg_block_count": (C.c_int, [_P, C.c_int]),
+    "hnhd_alg_block_meta": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "hnhd_alg_block_arrays": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "hnhd_dense_create": (C.c_int, [_I64, _I64, C.c_double, _PP]),
+    "hnhd_dense_like": (C.c_int, [_P, C.c_int, C.c_double, _PP]),
+    "hnhd_dense_fill": (C.c_int, [_P, C.c_double]),
+    "hnhd_dense_dummy_initialize": (C.c_int, [_P, _P, C.c_int]),
+    "hnhd_dense_from_host": (C.c_int, [_P, _P]),
+    "hnhd_dense_to_host": (C.c_int, [_P, _P]),
+    "hnhd_dense_shape": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hnhd_dense_data": (_P, [_P]),
+    "hnhd_dense_destroy": (None, [_P]),
+    "hnhd_vec_create": (C.c_int, [_I64, C.c_double, _PP]),
+    "hnhd_vec_like": (C.c_int, [_P, C.c_int, C.c_double, _PP]),
+    "hnhd_vec_fill": (C.c_int, [_P, C.c_double]),
+    "hnhd_vec_from_host": (C.c_int, [_P, _P]),
+    "hnhd_vec_to_host": (C.c_int, [_P, _P]),
+    "hnhd_vec_size": (C.c_int64, [_P]),
+    "hnhd_vec_destroy": (None, [_P]),
+    "hnhd_alg_op": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int]),
+    "hnhd_timer_start": (C.c_int, []),
+    "hnhd_timer_stop": (C.c_int, [C.POINTER(C.c_double)]),
+    "hnhd_benchmark_algorithm": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                           C.c_int, C.c_int, C.c_char_p, _SZ]),
+})

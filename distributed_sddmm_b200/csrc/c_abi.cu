@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -103,9 +104,10 @@ int launch_spmm(const int64_t *rowStart, const int64_t *col_idx, const double *v
 }
 template <int R, int G, int VW, int UN>
 int launch_fused(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
-                 const double *X, const double *Y, double *Out, bool beta0, cudaStream_t st) {
+                 const double *X, const double *Y, double *Out, bool bv, bool bo, cudaStream_t st) {
     int grid;
-    auto k = beta0 ? fused_row_kernel<R, G, VW, UN, true> : fused_row_kernel<R, G, VW, UN, false>;
+    auto k = bv ? (bo ? fused_row_kernel<R, G, VW, UN, true, true> : fused_row_kernel<R, G, VW, UN, true, false>)
+                : (bo ? fused_row_kernel<R, G, VW, UN, false, true> : fused_row_kernel<R, G, VW, UN, false, false>);
     int rc = grid_for(k, kBlock, kBlock / G, rows, &grid);
     if (rc) return rc;
     k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
@@ -122,6 +124,63 @@ int launch_sddmm_coo(const int64_t *row_idx, const int64_t *col_idx, double *val
     k<<<grid, kBlock, 0, st>>>(row_idx, col_idx, values, nnz, X, Y);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "sddmm_coo_kernel launch");
+}
+
+// ---- small-r ("split") launchers: G = GK*GN lanes per row ----------------------------------
+template <int R, int GK, int GN, int VW, int UN>
+int launch_sddmm_split(const int64_t *rowStart, const int64_t *col_idx, double *values,
+                       int64_t rows, const double *X, const double *Y, bool beta0, cudaStream_t st) {
+    int grid;
+    auto k = beta0 ? sddmm_split_kernel<R, GK, GN, VW, UN, true> : sddmm_split_kernel<R, GK, GN, VW, UN, false>;
+    int rc = grid_for(k, kBlock, kBlock / (GK * GN), rows, &grid);
+    if (rc) return rc;
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "sddmm_split_kernel launch");
+}
+template <int R, int GK, int GN, int VW, int UN>
+int launch_spmm_split(const int64_t *rowStart, const int64_t *col_idx, const double *values,
+                      int64_t rows, const double *X, double *Y, bool beta0, cudaStream_t st) {
+    int grid;
+    auto k = beta0 ? spmm_split_kernel<R, GK, GN, VW, UN, true> : spmm_split_kernel<R, GK, GN, VW, UN, false>;
+    int rc = grid_for(k, kBlock, kBlock / (GK * GN), rows, &grid);
+    if (rc) return rc;
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "spmm_split_kernel launch");
+}
+template <int R, int GK, int GN, int VW, int UN>
+int launch_fused_split(const int64_t *rowStart, const int64_t *col_idx, double *values,
+                       int64_t rows, const double *X, const double *Y, double *Out, bool bv, bool bo,
+                       cudaStream_t st) {
+    int grid;
+    auto k = bv ? (bo ? fused_split_kernel<R, GK, GN, VW, UN, true, true> : fused_split_kernel<R, GK, GN, VW, UN, true, false>)
+                : (bo ? fused_split_kernel<R, GK, GN, VW, UN, false, true> : fused_split_kernel<R, GK, GN, VW, UN, false, false>);
+    int rc = grid_for(k, kBlock, kBlock / (GK * GN), rows, &grid);
+    if (rc) return rc;
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "fused_split_kernel launch");
+}
+
+// Narrow factors (r <= split_max_r()) use the split kernels.  Shape table:
+// R -> (GK lanes across r, GN lanes across the row's nonzeros, VW, UN).
+#define HNH_DISPATCH_SPLIT(r, WIDE, CALL)                                                  \
+    switch (r) {                                                                          \
+        case 4:  if (WIDE) { CALL(4, 1, 8, 4, 4); } else { CALL(4, 2, 8, 2, 4); } break;   \
+        case 8:  if (WIDE) { CALL(8, 2, 8, 4, 4); } else { CALL(8, 4, 8, 2, 4); } break;   \
+        case 16: if (WIDE) { CALL(16, 4, 8, 4, 4); } else { CALL(16, 8, 4, 2, 4); } break; \
+        case 32: if (WIDE) { CALL(32, 8, 4, 4, 4); } else { CALL(32, 16, 2, 2, 4); } break;\
+        default: break;                                                                   \
+    }
+
+static int split_max_r() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HNH_SPLIT_MAX_R");
+        v = e ? atoi(e) : 32;
+    }
+    return v;
 }
 
 // Shape table: R -> (G lanes per row, VW doubles per vector load, UN rows in flight).
@@ -193,6 +252,11 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
             if (rc) return rc;
         }
         SGEN
+    } else if (r <= split_max_r() && r <= 32) {
+#define SP(R, GK, GN, VW, UN) \
+    rc = launch_sddmm_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, beta0, st)
+        HNH_DISPATCH_SPLIT(r, a32, SP)
+#undef SP
     } else {
         HNH_DISPATCH_R(r, a32, S4, S4, SGEN)
     }
@@ -265,6 +329,11 @@ int hnh_spmm_f64(const int64_t *rowStart, const int64_t *col_idx, const double *
             if (rc) return rc;
         }
         SGEN
+    } else if (r <= split_max_r() && r <= 32) {
+#define SP(R, GK, GN, VW, UN) \
+    rc = launch_spmm_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, beta0, st)
+        HNH_DISPATCH_SPLIT(r, a32, SP)
+#undef SP
     } else {
         HNH_DISPATCH_R(r, a32, S4, S4, SGEN)
     }
@@ -282,11 +351,14 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
     if (!X || !Y || !Out) return set_error(HNH_E_INVALID, "hnh_fused_f64: null dense operand");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = HNH_OK;
-    bool beta0 = (flags & HNH_FLAG_BETA0) != 0;
+    const bool bv = (flags & (HNH_FLAG_BETA0 | HNH_FLAG_BETA0_VALUES)) != 0;
+    const bool bo = (flags & (HNH_FLAG_BETA0 | HNH_FLAG_BETA0_OUT)) != 0;
+    if (X == Out && !bo)
+        return set_error(HNH_E_INVALID, "hnh_fused_f64: Out may alias X only when Out is overwritten (BETA0_OUT)");
     const bool a16 = aligned(X, 16) && aligned(Y, 16) && aligned(Out, 16);
     const bool a32 = aligned(X, 32) && aligned(Y, 32) && aligned(Out, 32);
 #define S4(R, G, VW, UN) \
-    rc = launch_fused<R, G, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, beta0, st)
+    rc = launch_fused<R, G, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)
 #define SGEN                                                                                 \
     {                                                                                        \
         int grid;                                                                            \
@@ -300,15 +372,18 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
     }
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
     if ((flags & HNH_FLAG_FORCE_GENERIC) || !a16 || !table_r) {
-        if (beta0) {
-            if (X == Out)
-                return set_error(HNH_E_INVALID, "hnh_fused_f64: in-place (Out == X) needs a table r "
-                                                "(4..256, power of two) and 16-byte aligned operands");
-            rc = check_cuda(cudaMemsetAsync(values, 0, sizeof(double) * (size_t)nnz, st), "cudaMemsetAsync");
-            if (!rc) rc = check_cuda(cudaMemsetAsync(Out, 0, sizeof(double) * (size_t)rows * r, st), "cudaMemsetAsync");
-            if (rc) return rc;
-        }
+        if (X == Out)
+            return set_error(HNH_E_INVALID, "hnh_fused_f64: in-place (Out == X) needs a table r "
+                                            "(4..256, power of two) and 16-byte aligned operands");
+        if (bv) rc = check_cuda(cudaMemsetAsync(values, 0, sizeof(double) * (size_t)nnz, st), "cudaMemsetAsync");
+        if (!rc && bo) rc = check_cuda(cudaMemsetAsync(Out, 0, sizeof(double) * (size_t)rows * r, st), "cudaMemsetAsync");
+        if (rc) return rc;
         SGEN
+    } else if (r <= split_max_r() && r <= 32) {
+#define SP(R, GK, GN, VW, UN) \
+    rc = launch_fused_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)
+        HNH_DISPATCH_SPLIT(r, a32, SP)
+#undef SP
     } else {
         HNH_DISPATCH_R(r, a32, S4, S4, SGEN)
     }
@@ -336,6 +411,11 @@ int hnh_fill_f64(double *dst, int64_t n, double value, void *stream) {
         return check_cuda(cudaMemsetAsync(dst, 0, sizeof(double) * (size_t)n, (cudaStream_t)stream),
                           "cudaMemsetAsync");
     HNH_ELEMENTWISE_LAUNCH(fill_kernel, n, dst, n, value);
+}
+
+int hnh_random_uniform_f64(double *dst, int64_t n, uint64_t seed, void *stream) {
+    if (n > 0 && !dst) return set_error(HNH_E_INVALID, "hnh_random_uniform_f64: null pointer");
+    HNH_ELEMENTWISE_LAUNCH(random_uniform_kernel, n, dst, n, seed);
 }
 
 int hnh_hadamard_f64(double *dst, const double *a, const double *b, int64_t n, void *stream) {
@@ -373,13 +453,13 @@ int hnh_row_axpy_f64(double *D, const double *C, double alpha, const double *s, 
                      int64_t rows, int r, void *stream) {
     if (rows < 0 || r <= 0) return set_error(HNH_E_INVALID, "hnh_row_axpy_f64: bad size");
     const int64_t n = rows * (int64_t)r;
-    if (n > 0 && (!D || !C || !M)) return set_error(HNH_E_INVALID, "hnh_row_axpy_f64: null pointer");
+    if (n > 0 && (!D || !M)) return set_error(HNH_E_INVALID, "hnh_row_axpy_f64: null pointer");
     HNH_ELEMENTWISE_LAUNCH(row_axpy_kernel, n, D, C, alpha, s, M, rows, r);
 }
 
 int hnh_vec_quotient_f64(double *out, const double *a, double ca, const double *b, double cb,
                          int64_t n, void *stream) {
-    if (n > 0 && (!out || !a || !b)) return set_error(HNH_E_INVALID, "hnh_vec_quotient_f64: null pointer");
+    if (n > 0 && (!out || !a)) return set_error(HNH_E_INVALID, "hnh_vec_quotient_f64: null pointer");
     HNH_ELEMENTWISE_LAUNCH(vec_quotient_kernel, n, out, a, ca, b, cb, n);
 }
 

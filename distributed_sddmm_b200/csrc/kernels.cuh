@@ -86,6 +86,13 @@ __device__ __forceinline__ double ld_stream_f64(const double *p) {
     return v;
 }
 
+// coherent (non-.nc) streaming load: for `values`, which the same kernel overwrites
+__device__ __forceinline__ double ld_rw_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
 template <int G>
 __device__ __forceinline__ unsigned group_mask(int lane) {
     if constexpr (G == 32) {
@@ -236,9 +243,9 @@ spmm_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict_
 
 // ------------------------------------------------------------------ K3: fused ------------
 // values[j] += X[row].Y[col_j];  Out[row] += sum_j values[j] * Y[col_j]; one gather per nnz.
-// BETA0: values = dot and Out = result (no read of the old contents); Out may then alias X
-// (each row of X is read only by the group that later writes that row of Out).
-template <int R, int G, int VW, int UN, bool BETA0>
+// BV: values = dot (old values not read).  BO: Out = result (old Out not read); Out may then
+// alias X (each row of X is read only by the group that later writes that row of Out).
+template <int R, int G, int VW, int UN, bool BV, bool BO>
 __global__ void __launch_bounds__(256)
 fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
                  double *__restrict__ values, int64_t rows, const double *X,
@@ -253,12 +260,12 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
          row += ngroups) {
         const int64_t s = ld_stream_i64(rowStart + row);
         const int64_t e = ld_stream_i64(rowStart + row + 1);
-        if (!BETA0 && s == e) continue;
+        if (!BO && s == e) continue;
         double x[NV][VW], acc[NV][VW];
 #pragma unroll
         for (int v = 0; v < NV; v++) {
             ld_rw<VW>(x[v], X + row * R + (v * G + gl) * VW);
-            if (BETA0) {
+            if (BO) {
 #pragma unroll
                 for (int w = 0; w < VW; w++) acc[v][w] = 0.0;
             } else {
@@ -271,7 +278,7 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
             double myval = 0.0;
             if (gl < cnt) {
                 mycol = ld_stream_i64(col_idx + j + gl);
-                if (!BETA0) myval = values[j + gl];
+                if (!BV) myval = values[j + gl];
             }
             for (int k0 = 0; k0 < cnt; k0 += UN) {
                 double y[UN][NV][VW];
@@ -316,6 +323,236 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
         }
 #pragma unroll
         for (int v = 0; v < NV; v++) st_rw<VW>(Out + row * R + (v * G + gl) * VW, acc[v]);
+    }
+}
+
+// ------------------------------------------------------------------ small-r kernels ------
+// For narrow factors (r <= 32) a row is too short to feed a whole warp, so the G = GK*GN lanes
+// that own a CSR row are laid out in two dimensions: GK lanes split the r columns (VW doubles
+// each, one vector load), GN lanes split the row's NONZEROS (lane np takes nonzeros
+// j0 + u*GN + np).  Consecutive lanes then read consecutive col_idx / values entries
+// (coalesced streams, no shuffle broadcast), every lane keeps UN gathers in flight, the r-wide
+// dot needs only log2(GK) shuffles, and SpMM's per-lane partial output rows are combined with
+// log2(GN) shuffles at the end of the row.  The summation order over a row's nonzeros is a
+// fixed tree (deterministic), not the oracle's sequential order.
+template <int G, int GK>
+__device__ __forceinline__ double reduce_over_k(double d, unsigned mask) {
+#pragma unroll
+    for (int o = GK / 2; o > 0; o >>= 1) d += __shfl_xor_sync(mask, d, o, G);
+    return d;
+}
+template <int G, int GK>
+__device__ __forceinline__ double reduce_over_n(double d, unsigned mask) {
+#pragma unroll
+    for (int o = GK; o < G; o <<= 1) d += __shfl_xor_sync(mask, d, o, G);
+    return d;
+}
+
+template <int R, int GK, int GN, int VW, int UN, bool BETA0>
+__global__ void __launch_bounds__(256)
+sddmm_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                   double *__restrict__ values, int64_t rows, const double *__restrict__ X,
+                   const double *__restrict__ Y) {
+    constexpr int G = GK * GN;
+    constexpr int NV = R / (GK * VW);
+    static_assert(NV * GK * VW == R && G <= 32, "bad split shape");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int kp = gl % GK, np = gl / GK;
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; row < rows;
+         row += ngroups) {
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        if (s == e) continue;
+        double x[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++) ld_gather<VW>(x[v], X + row * R + (v * GK + kp) * VW);
+        for (int64_t j0 = s; j0 < e; j0 += GN * UN) {
+            double y[UN][NV][VW];
+            double vold[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int64_t j = j0 + u * GN + np;
+                vold[u] = 0.0;
+                if (j < e) {
+                    const int64_t c = ld_stream_i64(col_idx + j);
+                    if (!BETA0) vold[u] = ld_rw_f64(values + j);
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+                        ld_gather<VW>(y[u][v], Y + c * R + (v * GK + kp) * VW);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) y[u][v][w] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int64_t j = j0 + u * GN + np;
+                double d = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+#pragma unroll
+                    for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
+                d = reduce_over_k<G, GK>(d, gmask);
+                if (j < e && kp == 0) values[j] = vold[u] + d;
+            }
+        }
+    }
+}
+
+template <int R, int GK, int GN, int VW, int UN, bool BETA0>
+__global__ void __launch_bounds__(256)
+spmm_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                  const double *__restrict__ values, int64_t rows, const double *__restrict__ X,
+                  double *__restrict__ Y) {
+    constexpr int G = GK * GN;
+    constexpr int NV = R / (GK * VW);
+    static_assert(NV * GK * VW == R && G <= 32, "bad split shape");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int kp = gl % GK, np = gl / GK;
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; row < rows;
+         row += ngroups) {
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        if (!BETA0 && s == e) continue;
+        double acc[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int w = 0; w < VW; w++) acc[v][w] = 0.0;
+        for (int64_t j0 = s; j0 < e; j0 += GN * UN) {
+            double xg[UN][NV][VW];
+            double vv[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int64_t j = j0 + u * GN + np;
+                if (j < e) {
+                    const int64_t c = ld_stream_i64(col_idx + j);
+                    vv[u] = ld_stream_f64(values + j);
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+                        ld_gather<VW>(xg[u][v], X + c * R + (v * GK + kp) * VW);
+                } else {
+                    vv[u] = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) xg[u][v][w] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++)
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+#pragma unroll
+                    for (int w = 0; w < VW; w++) acc[v][w] = fma(vv[u], xg[u][v][w], acc[v][w]);
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int w = 0; w < VW; w++) acc[v][w] = reduce_over_n<G, GK>(acc[v][w], gmask);
+        if (np == 0) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                if (!BETA0) {
+                    double old[VW];
+                    ld_rw<VW>(old, Y + row * R + (v * GK + kp) * VW);
+#pragma unroll
+                    for (int w = 0; w < VW; w++) acc[v][w] += old[w];
+                }
+                st_rw<VW>(Y + row * R + (v * GK + kp) * VW, acc[v]);
+            }
+        }
+    }
+}
+
+template <int R, int GK, int GN, int VW, int UN, bool BV, bool BO>
+__global__ void __launch_bounds__(256)
+fused_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
+                   double *__restrict__ values, int64_t rows, const double *X,
+                   const double *__restrict__ Y, double *Out) {
+    constexpr int G = GK * GN;
+    constexpr int NV = R / (GK * VW);
+    static_assert(NV * GK * VW == R && G <= 32, "bad split shape");
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int kp = gl % GK, np = gl / GK;
+    const unsigned gmask = group_mask<G>(lane);
+    const int64_t ngroups = (int64_t)gridDim.x * (blockDim.x / G);
+    for (int64_t row = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; row < rows;
+         row += ngroups) {
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        if (!BO && s == e) continue;
+        double x[NV][VW], acc[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            ld_rw<VW>(x[v], X + row * R + (v * GK + kp) * VW);
+#pragma unroll
+            for (int w = 0; w < VW; w++) acc[v][w] = 0.0;
+        }
+        for (int64_t j0 = s; j0 < e; j0 += GN * UN) {
+            double y[UN][NV][VW];
+            double vold[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int64_t j = j0 + u * GN + np;
+                vold[u] = 0.0;
+                if (j < e) {
+                    const int64_t c = ld_stream_i64(col_idx + j);
+                    if (!BV) vold[u] = ld_rw_f64(values + j);
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+                        ld_gather<VW>(y[u][v], Y + c * R + (v * GK + kp) * VW);
+                } else {
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) y[u][v][w] = 0.0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const int64_t j = j0 + u * GN + np;
+                double d = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; v++)
+#pragma unroll
+                    for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
+                d = reduce_over_k<G, GK>(d, gmask);
+                const double vnew = vold[u] + d;
+                if (j < e) {
+                    if (kp == 0) values[j] = vnew;
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int w = 0; w < VW; w++) acc[v][w] = fma(vnew, y[u][v][w], acc[v][w]);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int w = 0; w < VW; w++) acc[v][w] = reduce_over_n<G, GK>(acc[v][w], gmask);
+        if (np == 0) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                if (!BO) {
+                    double old[VW];
+                    ld_rw<VW>(old, Out + row * R + (v * GK + kp) * VW);
+#pragma unroll
+                    for (int w = 0; w < VW; w++) acc[v][w] += old[w];
+                }
+                st_rw<VW>(Out + row * R + (v * GK + kp) * VW, acc[v]);
+            }
+        }
     }
 }
 
@@ -474,6 +711,18 @@ __global__ void fill_kernel(double *__restrict__ dst, int64_t n, double value) {
         dst[i] = value;
 }
 
+// uniform(-1, 1) from a counter-based hash of (seed, i): Eigen's setRandom() stand-in
+__global__ void random_uniform_kernel(double *__restrict__ dst, int64_t n, uint64_t seed) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t z = seed + (uint64_t)i * 0x9E3779B97F4A7C15ull + 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        dst[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
+
 __global__ void hadamard_kernel(double *__restrict__ dst, const double *__restrict__ a,
                                 const double *__restrict__ b, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -513,7 +762,7 @@ __global__ void row_axpy_kernel(double *D, const double *C, double alpha,
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double sc = s ? s[i / r] : 1.0;
-        D[i] = C[i] + alpha * sc * M[i];
+        D[i] = (C ? C[i] : 0.0) + alpha * sc * M[i];
     }
 }
 
@@ -521,7 +770,7 @@ __global__ void vec_quotient_kernel(double *out, const double *a, double ca, con
                                     double cb, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = (a[i] + ca) / (b[i] + cb);
+        out[i] = b ? (a[i] + ca) / (b[i] + cb) : (a[i] + ca);
 }
 
 __global__ void axpby_kernel(double *dst, double alpha, const double *x, double beta,

@@ -1,0 +1,186 @@
+// runtime.cpp -- implementation of hnh::Runtime, EventTimers and the error helpers.
+#include "hnh/runtime.h"
+
+#include "hnh_b200.h"
+
+namespace hnh {
+
+void cuda_check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess)
+        throw Error(e == cudaErrorMemoryAllocation ? HNH_E_ALLOC : HNH_E_CUDA,
+                    std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+void abi_check(int rc, const char *what) {
+    if (rc != HNH_OK) throw Error(rc, std::string(what) + ": " + hnh_last_error_string());
+}
+
+Runtime &Runtime::get() {
+    static Runtime r;
+    return r;
+}
+
+void Runtime::init() {
+    if (inited_) return;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        throw Error(HNH_E_CUDA, "no CUDA device: the hnh_b200 host library has no CPU path");
+    cuda_check(cudaGetDevice(&dev_), "cudaGetDevice");
+    cuda_check(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking), "cudaStreamCreate");
+    cuda_check(cudaStreamCreateWithFlags(&comm_, cudaStreamNonBlocking), "cudaStreamCreate");
+    chain_events_.resize(64);
+    for (auto &ev : chain_events_)
+        cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+    inited_ = true;
+}
+
+bool Runtime::has_device() {
+    if (inited_) return true;
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess && n > 0;
+}
+
+cudaStream_t Runtime::compute_stream() { init(); return compute_; }
+cudaStream_t Runtime::comm_stream() { init(); return comm_; }
+int Runtime::device() { init(); return dev_; }
+
+void Runtime::chain(cudaStream_t signaler, cudaStream_t waiter) {
+    init();
+    if (signaler == waiter) return;
+    cudaEvent_t ev = chain_events_[chain_next_++ % chain_events_.size()];
+    cuda_check(cudaEventRecord(ev, signaler), "cudaEventRecord");
+    cuda_check(cudaStreamWaitEvent(waiter, ev, 0), "cudaStreamWaitEvent");
+}
+
+void Runtime::sync_all() {
+    if (!inited_) return;
+    cuda_check(cudaStreamSynchronize(compute_), "sync compute");
+    cuda_check(cudaStreamSynchronize(comm_), "sync comm");
+}
+
+void *Runtime::alloc(size_t bytes) {
+    init();
+    void *p = nullptr;
+    const size_t b = bytes ? ((bytes + 255) & ~(size_t)255) : 256;
+    auto it = cache_.find(b);
+    if (it != cache_.end() && !it->second.empty()) {
+        p = it->second.back();
+        it->second.pop_back();
+        return p;
+    }
+    cudaError_t e = cudaMalloc(&p, b);
+    if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
+        cudaGetLastError();
+        trim();
+        e = cudaMalloc(&p, b);
+    }
+    cuda_check(e, "cudaMalloc");
+    sizes_[p] = b;
+    allocated_ += b;
+    return p;
+}
+
+void Runtime::free(void *p) {
+    if (!p) return;
+    auto it = sizes_.find(p);
+    if (it == sizes_.end()) {
+        cudaFree(p);
+        return;
+    }
+    cache_[it->second].push_back(p);
+}
+
+void Runtime::trim() {
+    for (auto &kv : cache_)
+        for (void *p : kv.second) {
+            allocated_ -= kv.first;
+            sizes_.erase(p);
+            cudaFree(p);
+        }
+    cache_.clear();
+}
+
+void *Runtime::alloc_pinned(size_t bytes) {
+    init();
+    void *p = nullptr;
+    cuda_check(cudaMallocHost(&p, bytes ? bytes : 256), "cudaMallocHost");
+    return p;
+}
+
+void Runtime::free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- EventTimers ------------
+EventTimers::~EventTimers() {
+    for (auto &kv : spans_)
+        for (auto &s : kv.second) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+    for (auto ev : pool_) cudaEventDestroy(ev);
+}
+
+cudaEvent_t EventTimers::get_event() {
+    if (!pool_.empty()) {
+        cudaEvent_t ev = pool_.back();
+        pool_.pop_back();
+        return ev;
+    }
+    cudaEvent_t ev;
+    cuda_check(cudaEventCreate(&ev), "cudaEventCreate");
+    return ev;
+}
+
+void EventTimers::start(const std::string &key, cudaStream_t s) {
+    cudaEvent_t ev = get_event();
+    cuda_check(cudaEventRecord(ev, s), "cudaEventRecord");
+    open_[key] = ev;
+}
+
+void EventTimers::stop(const std::string &key, cudaStream_t s) {
+    auto it = open_.find(key);
+    if (it == open_.end()) throw Error(HNH_E_INVALID, "EventTimers::stop without start: " + key);
+    cudaEvent_t b = get_event();
+    cuda_check(cudaEventRecord(b, s), "cudaEventRecord");
+    spans_[key].push_back({it->second, b});
+    counts_[key]++;
+    open_.erase(it);
+}
+
+void EventTimers::reset() {
+    for (auto &kv : spans_)
+        for (auto &s : kv.second) {
+            pool_.push_back(s.a);
+            pool_.push_back(s.b);
+        }
+    spans_.clear();
+    resolved_.clear();
+    counts_.clear();
+}
+
+double EventTimers::total_seconds(const std::string &key) {
+    auto it = spans_.find(key);
+    if (it != spans_.end()) {
+        double ms = 0.0;
+        for (auto &s : it->second) {
+            cuda_check(cudaEventSynchronize(s.b), "cudaEventSynchronize");
+            float t = 0.f;
+            cuda_check(cudaEventElapsedTime(&t, s.a, s.b), "cudaEventElapsedTime");
+            ms += t;
+            pool_.push_back(s.a);
+            pool_.push_back(s.b);
+        }
+        it->second.clear();
+        resolved_[key] += ms * 1e-3;
+    }
+    return resolved_[key];
+}
+
+int EventTimers::count(const std::string &key) const {
+    auto it = counts_.find(key);
+    return it == counts_.end() ? 0 : it->second;
+}
+
+}  // namespace hnh

@@ -1,0 +1,61 @@
+// sparse_kernels.cpp -- StandardKernel on the sm_100a kernels (hnh_b200.h C ABI).
+#include "hnh/sparse_kernels.h"
+
+#include "hnh_b200.h"
+
+using hnh::abi_check;
+using hnh::Runtime;
+
+size_t StandardKernel::sddmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B, int block, int /*offset*/) {
+    if (A.cols() != B.cols()) throw hnh::Error(HNH_E_INVALID, "sddmm_local: A.cols() != B.cols()");
+    CSRLocal *blk = S.csr_blocks[block];
+    if (blk == nullptr || blk->num_coords == 0) return 0;
+    // role swap on transposed storage (reference sparse_kernels.cpp:29-38)
+    const double *X = blk->transpose ? B.data() : A.data();
+    const double *Y = blk->transpose ? A.data() : B.data();
+    CSRHandle *h = blk->getActive();
+    int f = flags | (values_are_zero ? HNH_FLAG_BETA0 : 0);
+    abi_check(hnh_sddmm_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords, X, Y,
+                            (int)A.cols(), f, Runtime::get().compute_stream()),
+              "hnh_sddmm_f64");
+    return 0;
+}
+
+size_t StandardKernel::spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B, MatMode mode, int block) {
+    CSRLocal *blk = S.csr_blocks[block];
+    if (output_is_zero && (blk == nullptr || blk->num_coords == 0)) {
+        // "overwrite" hint on an empty block: the output of this step is all zeros
+        ((mode == Amat) ? A : B).setZero();
+        return 0;
+    }
+    if (blk == nullptr) return 0;
+    if (mode == Amat && blk->transpose)
+        throw hnh::Error(HNH_E_MODE, "Error, local matrix is transposed, can't perform SpmmA");
+    if (mode == Bmat && !blk->transpose)
+        throw hnh::Error(HNH_E_MODE, "Error, local matrix is not transposed, can't perform SpmmB");
+    if (blk->num_coords == 0) return 0;
+    const double *In = (mode == Amat) ? B.data() : A.data();
+    double *Out = (mode == Amat) ? A.data() : B.data();
+    CSRHandle *h = blk->getActive();
+    int f = flags | (output_is_zero ? HNH_FLAG_BETA0 : 0);
+    abi_check(hnh_spmm_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords, In, Out,
+                           (int)A.cols(), f, Runtime::get().compute_stream()),
+              "hnh_spmm_f64");
+    return 0;
+}
+
+size_t StandardKernel::fused_local(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block,
+                                   bool first_visit, bool out_is_zero) {
+    CSRLocal *blk = S.csr_blocks[block];
+    if (blk == nullptr || blk->num_coords == 0) {
+        if (out_is_zero) Out.setZero();
+        return 0;
+    }
+    if (blk->transpose) throw hnh::Error(HNH_E_MODE, "fused_local needs a non-transposed block");
+    CSRHandle *h = blk->getActive();
+    int f = flags | (first_visit ? HNH_FLAG_BETA0_VALUES : 0) | (out_is_zero ? HNH_FLAG_BETA0_OUT : 0);
+    abi_check(hnh_fused_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords,
+                            X.data(), B.data(), Out.data(), (int)X.cols(), f, Runtime::get().compute_stream()),
+              "hnh_fused_f64");
+    return 0;
+}

@@ -1,0 +1,218 @@
+// hnh/15D_dense_shift.hpp -- 1.5D dense-shifting algorithm (Sparse15D_Dense_Shift) on B200s.
+//
+// Layout and data flow follow the reference (15D_dense_shift.hpp:22-385, SURVEY.md
+// appendix A.1): grid (p/c) x c, adjacency 1; rank (i, j) owns dense row block c*i + j of A and
+// of B; S is split by block rows of height ceil(M/p)*c and cyclic block columns (only column
+// blocks == j mod c are non-empty on rank (i, j)); the stationary dense operand is replicated
+// over row_world (size c) and the other one rides a ring over col_world (size p/c).
+// fusionApproach 1 = "replication reuse" (blocks stored transposed, the SpMM OUTPUT rides);
+// fusionApproach 2 = "local kernel fusion" (blocks not transposed, inputs ride, the output is
+// reduce-scattered) with its own fusedSpMM.
+//
+// What is new here: device-resident operands; NCCL all-gather / reduce-scatter / ring
+// send-recv on a communication stream overlapped with the kernels wherever the riding matrix
+// is an input (Distributed_Sparse::ring_dense); one fused SDDMM->SpMM CUDA kernel per ring step
+// in the fusion-2 fusedSpMM; persistent replication / accumulation buffers; no per-call
+// allocation, zero-fill or copy-back passes that the arithmetic does not need.
+#pragma once
+#include <memory>
+
+#include "hnh/distributed_sparse.h"
+
+class ShardedBlockCyclicColumn : public NonzeroDistribution {
+public:
+    int p, c;
+    shared_ptr<FlexibleGrid> grid;
+    ShardedBlockCyclicColumn(int M, int N, int p, int c, shared_ptr<FlexibleGrid> &grid) {
+        world = hnh::Comm::world();
+        this->p = p;
+        this->c = c;
+        this->grid = grid;
+        rows_in_block = divideAndRoundUp(M, p) * c;
+        cols_in_block = divideAndRoundUp(N, p);
+    }
+    int blockOwner(int row_block, int col_block) override { return grid->get_global_rank(row_block, col_block % c, 0); }
+};
+
+class Sparse15D_Dense_Shift : public Distributed_Sparse {
+public:
+    int fusionApproach;
+    DenseMatrix accumulation_buffer;  // gathered stationary operand, or the SpMM accumulator
+    DenseMatrix broadcast_buffer;     // fusion-2 fusedSpMM: gathered stationary operand
+
+    Sparse15D_Dense_Shift(SpmatLocal *S_input, int R, int c, int fusionApproach, KernelImplementation *k)
+        : Distributed_Sparse(k) {
+        this->fusionApproach = fusionApproach;
+        this->c = c;
+        if (c < 1 || p % c != 0) throw hnh::Error(-1, "Error, for 1.5D algorithm, must have c divide num_procs!");
+        if (fusionApproach != 1 && fusionApproach != 2) throw hnh::Error(-1, "fusionApproach must be 1 or 2");
+
+        algorithm_name = "1.5D Block Row Replicated S Striped AB Cyclic Shift";
+        proc_grid_names = {"# Rows", "# Layers"};
+        perf_counter_keys = {"Replication Time", "Cyclic Shift Time", "Computation Time"};
+        grid.reset(new FlexibleGrid(p / c, c, 1, 1));
+        r_split = false;
+        M = (int64_t)S_input->M;
+        N = (int64_t)S_input->N;
+
+        ShardedBlockCyclicColumn standard_dist((int)M, (int)N, p, c, grid);
+        ShardedBlockCyclicColumn transpose_dist((int)N, (int)M, p, c, grid);
+        S.reset(S_input->redistribute_nonzeros(&standard_dist, false, false));
+        ST.reset(S->redistribute_nonzeros(&transpose_dist, true, false));
+
+        localArows = divideAndRoundUp((int)M, p);
+        localBrows = divideAndRoundUp((int)N, p);
+        setRValue(R);
+
+        localise(*S, localArows * c, localBrows);
+        localise(*ST, localBrows * c, localArows);
+        const bool local_tpose = fusionApproach == 1;
+        S->initializeCSRBlocks(localArows * c, localBrows, -1, local_tpose);
+        vector<spcoord_t>().swap(S->coords);
+        ST->initializeCSRBlocks(localBrows * c, localArows, -1, local_tpose);
+        vector<spcoord_t>().swap(ST->coords);
+        check_initialized();
+    }
+
+    void setRValue(int R) override {
+        this->R = R;
+        localAcols = R;
+        localBcols = R;
+        aSubmatrices.clear();
+        bSubmatrices.clear();
+        aSubmatrices.emplace_back(localArows * (c * grid->i + grid->j), 0, localArows, localAcols);
+        bSubmatrices.emplace_back(localBrows * (c * grid->i + grid->j), 0, localBrows, localBcols);
+    }
+
+    void initial_shift(DenseMatrix *, DenseMatrix *, KernelMode) override {}
+    void de_shift(DenseMatrix *, DenseMatrix *, KernelMode) override {}
+
+    // fusion 1 keeps the values of an A-mode operation in ST's order (reference :254-270)
+    int64_t num_S_values() override {
+        SpmatLocal &m = fusionApproach == 1 ? *ST : *S;
+        return m.owned_coords_end - m.owned_coords_start;
+    }
+    int64_t num_ST_values() override {
+        SpmatLocal &m = fusionApproach == 1 ? *S : *ST;
+        return m.owned_coords_end - m.owned_coords_start;
+    }
+
+    // block of S / ST that meets the riding shard at ring step `step`
+    int block_at(int step) const { return pMod((grid->rankInCol - step) * c + grid->rankInRow, p); }
+
+    void algorithm(DenseMatrix &localA, DenseMatrix &localB, VectorXd &SValues, VectorXd *sddmm_result_ptr,
+                   KernelMode mode, bool initial_replicate) override {
+        const bool a_mode = (mode == k_spmmA || mode == k_sddmmA);
+        const bool sddmm = (mode == k_sddmmA || mode == k_sddmmB);
+        // fusion 1 works on the transposed problem: for an A-mode operation the stationary
+        // (replicated) operand is B and A rides; fusion 2 is the other way round.
+        const bool swap_roles = (fusionApproach == 1) == a_mode;
+        DenseMatrix *stationary = swap_roles ? &localB : &localA;
+        DenseMatrix *riding = swap_roles ? &localA : &localB;
+        SpmatLocal *choice = swap_roles ? ST.get() : S.get();
+        StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
+
+        if (initial_replicate && c > 1) replicate(*stationary, accumulation_buffer);
+        DenseMatrix &fixed = c > 1 ? accumulation_buffer : *stationary;
+
+        region_begin("Computation Time", compute());
+        if (sddmm) {
+            if (!sk) choice->setValuesConstant(0.0);  // StandardKernel overwrites instead (every block is met once)
+        } else {
+            choice->setCSRValues(SValues);
+        }
+        region_end("Computation Time", compute());
+
+        KernelMode local_mode = mode;
+        if (fusionApproach == 1 && mode == k_spmmA) local_mode = k_spmmB;
+        if (fusionApproach == 2 && mode == k_spmmB) local_mode = k_spmmA;
+        // the riding matrix is written only by the fusion-1 SpMM (it is the output there)
+        const bool riding_is_input = sddmm || fusionApproach == 2;
+
+        ring_dense(*riding, *grid->col_world, riding_is_input, "Cyclic Shift Time", "Computation Time",
+                   [&](int step, DenseMatrix &shard) {
+                       if (sk) sk->values_are_zero = sddmm;
+                       kernel->triple_function(local_mode, *choice, fixed, shard, block_at(step), 0);
+                       if (sk) sk->values_are_zero = false;
+                   });
+
+        if (sddmm) {
+            region_begin("Computation Time", compute());
+            hadamard_values(*sddmm_result_ptr, SValues, *choice);
+            region_end("Computation Time", compute());
+        }
+        if (fusionApproach == 2 && !sddmm && c > 1) reduce_to(*stationary, accumulation_buffer);
+    }
+
+    // Local kernel fusion: one pass over the ring doing SDDMM and SpMM on each block.
+    // Like the reference (15D_dense_shift.hpp:189,250-251) this variant treats S as an all-ones
+    // pattern (Svalues ignored) and does not fill sddmm_buffer; the block values it leaves in
+    // the CSR are the SDDMM result.
+    void fusedSpMM(DenseMatrix &localA, DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer,
+                   MatMode mode) override {
+        if (fusionApproach == 1) {
+            Distributed_Sparse::fusedSpMM(localA, localB, Svalues, sddmm_buffer, mode);
+            return;
+        }
+        DenseMatrix *stationary = mode == Amat ? &localA : &localB;
+        DenseMatrix *riding = mode == Amat ? &localB : &localA;
+        SpmatLocal *choice = mode == Amat ? S.get() : ST.get();
+        StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
+        const int steps = p / c;
+
+        if (c > 1) replicate(*stationary, broadcast_buffer);
+        DenseMatrix &gathered = c > 1 ? broadcast_buffer : *stationary;
+        // With one ring step and no replication the output row i depends only on input row i:
+        // the fused kernel may then write the result over its own input.
+        const bool in_place = sk && steps == 1 && c == 1;
+        if (!in_place) accumulation_buffer.resize(gathered.rows(), gathered.cols());
+        DenseMatrix &out = in_place ? *stationary : accumulation_buffer;
+        if (!sk) {
+            region_begin("Computation Time", compute());
+            choice->setValuesConstant(0.0);
+            out.setZero();
+            region_end("Computation Time", compute());
+        }
+
+        ring_dense(*riding, *grid->col_world, true, "Cyclic Shift Time", "Computation Time",
+                   [&](int step, DenseMatrix &shard) {
+                       kernel->fused_local(*choice, gathered, shard, out, block_at(step), sk != nullptr,
+                                           sk != nullptr && step == 0);
+                   });
+
+        if (c > 1) {
+            reduce_to(*stationary, accumulation_buffer);
+        } else if (!in_place) {
+            stationary->swap(accumulation_buffer);  // instead of `*Arole = accumulation_buffer`
+        }
+    }
+
+private:
+    static void localise(SpmatLocal &m, int block_rows, int block_cols) {
+#pragma omp parallel for
+        for (int64_t i = 0; i < (int64_t)m.coords.size(); i++) m.coords[i].r %= (uint64_t)block_rows;
+        m.divideIntoBlockCols(block_cols, hnh::Comm::world()->size(), true);
+        m.own_all_coordinates();
+    }
+
+    // all-gather `local` over row_world into `gathered` (rows * c)
+    void replicate(DenseMatrix &local, DenseMatrix &gathered) {
+        hnh::Runtime &rt = hnh::Runtime::get();
+        gathered.resize(local.rows() * c, local.cols());
+        rt.chain(compute(), comm());
+        region_begin("Replication Time", comm());
+        grid->row_world->allgather(local.data(), gathered.data(), sizeof(double) * (size_t)local.size(), comm());
+        region_end("Replication Time", comm());
+        rt.chain(comm(), compute());
+    }
+
+    // reduce-scatter `partial` (rows * c) over row_world into `local`
+    void reduce_to(DenseMatrix &local, DenseMatrix &partial) {
+        hnh::Runtime &rt = hnh::Runtime::get();
+        rt.chain(compute(), comm());
+        region_begin("Replication Time", comm());
+        grid->row_world->reduce_scatter_sum_f64(partial.data(), local.data(), (size_t)local.size(), comm());
+        region_end("Replication Time", comm());
+        rt.chain(comm(), compute());
+    }
+};

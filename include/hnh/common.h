@@ -1,0 +1,182 @@
+// hnh/common.h -- common types of the B200-native HnH host library.
+//
+// Mirrors the public surface of the reference's common.h / common.cpp (DenseMatrix, MatMode,
+// spcoord_t, BufferPair, pMod, divideAndRoundUp, divideIntoSegments, start_clock /
+// stop_clock_get_elapsed; reference common.h:13-93, common.cpp:6-84) with one decisive
+// difference: DenseMatrix and VectorXd own DEVICE memory (HBM) and every operation on them is a
+// stream-ordered CUDA launch on hnh::Runtime::compute_stream().  The reference's DenseMatrix is
+// an Eigen row-major host matrix (common.h:13); only the subset of the Eigen API that the
+// reference's own callers use on the hot path and in the ALS application is provided
+// (SURVEY.md 8b lists it).  `data()` returns a device pointer.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "hnh/runtime.h"
+
+using namespace std;  // the reference's headers do this and its drivers rely on it
+
+typedef chrono::time_point<std::chrono::steady_clock> my_timer_t;
+my_timer_t start_clock();
+double stop_clock_get_elapsed(my_timer_t &start);
+
+typedef enum { Amat, Bmat } MatMode;
+
+int pMod(int num, int denom);
+int divideAndRoundUp(int num, int denom);
+// Roughly equal segments; segment_starts has num_segments + 1 entries (common.cpp:68-84).
+void divideIntoSegments(int total, int num_segments, vector<int> &segment_starts,
+                        vector<int> &segment_sizes);
+
+struct spcoord_t {
+    uint64_t r;
+    uint64_t c;
+    double value;
+    string string_rep() const;
+};
+bool column_major(const spcoord_t &a, const spcoord_t &b);  // sort by (c, r)
+bool row_major(const spcoord_t &a, const spcoord_t &b);     // sort by (r, c)
+inline void initialize_mpi_datatypes() {}  // SPCOORD is sent as raw bytes here (common.cpp:37-47)
+
+class DenseMatrix;
+
+// Device vector of doubles (the reference's Eigen::VectorXd of SValues / sddmm_result).
+class VectorXd {
+public:
+    VectorXd() = default;
+    explicit VectorXd(int64_t n) : buf_((size_t)n), n_(n) {}
+    VectorXd(const VectorXd &o);
+    VectorXd &operator=(const VectorXd &o);
+    VectorXd(VectorXd &&) = default;
+    VectorXd &operator=(VectorXd &&) = default;
+    static VectorXd Constant(int64_t n, double value);
+
+    int64_t size() const { return n_; }
+    double *data() { return buf_.data(); }
+    const double *data() const { return buf_.data(); }
+    void resize(int64_t n) { buf_.resize((size_t)n); n_ = n; }
+    void setZero() { setConstant(0.0); }
+    void setConstant(double v);
+
+    VectorXd cwiseProduct(const VectorXd &o) const;
+    VectorXd cwiseQuotient(const VectorXd &o) const;
+    VectorXd operator+(const VectorXd &o) const;
+    VectorXd operator-(const VectorXd &o) const;
+    VectorXd &operator+=(double c);  // `.array() += c` of the reference
+    double squaredNorm() const;      // synchronises and returns the host value
+    double sum() const;
+    // this[i] = (a[i] + ca) / (b[i] + cb): the alpha/coeff updates of cg_optimizer
+    void setQuotient(const VectorXd &a, double ca, const VectorXd &b, double cb);
+
+    // host interop (not in Eigen; the data lives in HBM)
+    static VectorXd from_host(const double *h, int64_t n);
+    vector<double> to_host() const;
+    void copy_from_host(const double *h);
+    void swap(VectorXd &o) { buf_.swap(o.buf_); std::swap(n_, o.n_); }
+
+private:
+    hnh::DeviceBuffer<double> buf_;
+    int64_t n_ = 0;
+};
+
+// A contiguous block of rows of a DenseMatrix (what Eigen's middleRows returns).
+struct RowBlock {
+    double *ptr;
+    int64_t nrows, ncols;
+    RowBlock &operator=(const DenseMatrix &m);  // copy m into the block
+    double *data() const { return ptr; }
+    int64_t rows() const { return nrows; }
+    int64_t cols() const { return ncols; }
+    int64_t size() const { return nrows * ncols; }
+};
+
+// Row-major dense matrix of doubles in HBM, leading dimension = cols().
+class DenseMatrix {
+public:
+    DenseMatrix() = default;
+    DenseMatrix(int64_t rows, int64_t cols) : buf_((size_t)(rows * cols)), rows_(rows), cols_(cols) {}
+    DenseMatrix(const DenseMatrix &o);
+    DenseMatrix &operator=(const DenseMatrix &o);
+    DenseMatrix(DenseMatrix &&) = default;
+    DenseMatrix &operator=(DenseMatrix &&) = default;
+    DenseMatrix(const RowBlock &b);  // copy out of a block
+    DenseMatrix &operator=(const RowBlock &b);
+    static DenseMatrix Constant(int64_t rows, int64_t cols, double value);
+    // Non-owning view of rows x cols doubles at device pointer p (e.g. a row block of another
+    // matrix): lets a kernel work on part of a matrix without the copies Eigen's
+    // `tmp = X.middleRows(...)` / `X.middleRows(...) = tmp` make (15D_sparse_shift.hpp:232-249).
+    static DenseMatrix view(double *p, int64_t rows, int64_t cols) {
+        DenseMatrix m;
+        m.buf_.adopt(p, (size_t)(rows * cols));
+        m.rows_ = rows;
+        m.cols_ = cols;
+        return m;
+    }
+    DenseMatrix rowsView(int64_t start, int64_t n) { return view(buf_.data() + start * cols_, n, cols_); }
+
+    int64_t rows() const { return rows_; }
+    int64_t cols() const { return cols_; }
+    int64_t size() const { return rows_ * cols_; }
+    double *data() { return buf_.data(); }
+    const double *data() const { return buf_.data(); }
+    void resize(int64_t rows, int64_t cols);
+    void setZero() { setConstant(0.0); }
+    void setConstant(double v);
+    void setRandom(uint64_t seed);  // uniform(-1, 1), counter-based (Eigen::setRandom)
+    RowBlock middleRows(int64_t start, int64_t n) {
+        return RowBlock{buf_.data() + start * cols_, n, cols_};
+    }
+
+    DenseMatrix &operator*=(double s);
+    DenseMatrix &operator/=(double s) { return *this *= (1.0 / s); }
+    DenseMatrix &operator+=(const DenseMatrix &o);
+    DenseMatrix &operator-=(const DenseMatrix &o);
+    DenseMatrix operator+(const DenseMatrix &o) const;
+    DenseMatrix operator-(const DenseMatrix &o) const;
+    DenseMatrix cwiseProduct(const DenseMatrix &o) const;
+    double squaredNorm() const;
+
+    // this = c + alpha * diag(s) * m  (row-scaled axpy; s empty == all ones). In place allowed.
+    void setRowAxpy(const DenseMatrix &c, double alpha, const VectorXd *s, const DenseMatrix &m);
+
+    static DenseMatrix from_host(const double *h, int64_t rows, int64_t cols);
+    vector<double> to_host() const;
+    void copy_from_host(const double *h);
+    void swap(DenseMatrix &o) { buf_.swap(o.buf_); std::swap(rows_, o.rows_); std::swap(cols_, o.cols_); }
+
+private:
+    hnh::DeviceBuffer<double> buf_;
+    int64_t rows_ = 0, cols_ = 0;
+};
+
+// batch_dot_product / scale_matrix_rows of als_conjugate_gradients.cpp:9-29 on the device
+VectorXd batch_dot_product(const DenseMatrix &A, const DenseMatrix &B);
+DenseMatrix scale_matrix_rows(const VectorXd &scale_vector, const DenseMatrix &mat);
+
+// Double buffer for ring shifts (reference common.h:49-93).  `extra` comes from the caching
+// allocator; sync_active() swaps storage instead of copying when the live data ended up in
+// `extra`.
+class BufferPair {
+public:
+    DenseMatrix *original;
+    DenseMatrix *extra;
+    int switchVal;
+
+    explicit BufferPair(DenseMatrix *buf)
+        : original(buf), extra(new DenseMatrix(buf->rows(), buf->cols())), switchVal(0) {}
+    ~BufferPair() { delete extra; }
+    BufferPair(const BufferPair &) = delete;
+    BufferPair &operator=(const BufferPair &) = delete;
+    DenseMatrix *getActive() { return switchVal == 0 ? original : extra; }
+    DenseMatrix *getPassive() { return switchVal == 0 ? extra : original; }
+    void swapActive() { switchVal = 1 - switchVal; }
+    void sync_active() {
+        if (switchVal == 1) {
+            original->swap(*extra);
+            switchVal = 0;
+        }
+    }
+};

@@ -44,6 +44,9 @@ extern "C" {
  * output first (setValuesConstant(0) / setZero(), SpmatLocal.hpp:595-605,
  * distributed_sparse.h:275) but without the extra pass over memory. */
 #define HNH_FLAG_BETA0 4
+/* fused only: overwrite just the values (each block is visited once per FusedMM) or just Out */
+#define HNH_FLAG_BETA0_VALUES 16
+#define HNH_FLAG_BETA0_OUT 32
 
 /* ABI / build identification. */
 int hnh_abi_version(void);
@@ -89,6 +92,9 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
 
 /* ---- K4: value plumbing (SpmatLocal.hpp:571-605, 15D_dense_shift.hpp:366) -------------- */
 int hnh_fill_f64(double *dst, int64_t n, double value, void *stream);
+/* dst[i] = uniform(-1,1) from a counter-based hash of (seed, i) -- DenseMatrix::setRandom
+ * (als_conjugate_gradients.cpp:143-146) */
+int hnh_random_uniform_f64(double *dst, int64_t n, uint64_t seed, void *stream);
 /* dst[i] = a[i] * b[i]  (VectorXd::cwiseProduct of SValues and getCSRValues()) */
 int hnh_hadamard_f64(double *dst, const double *a, const double *b, int64_t n, void *stream);
 /* row_idx[i] = CSR row of nonzero i (SpmatLocal.hpp:139-147,160-163) */
@@ -101,10 +107,10 @@ int hnh_expand_row_idx(const int64_t *rowStart, int64_t rows, int64_t nnz, int64
 int hnh_batch_dot_f64(double *out, const double *A, const double *B, int64_t rows, int r,
                       void *stream);
 /* D[i,k] = C[i,k] + alpha * s[i] * M[i,k]   (X += scale_matrix_rows(s, M) and friends;
- * s may be NULL meaning all-ones; D may alias C or M) */
+ * s may be NULL meaning all-ones; C may be NULL meaning zero; D may alias C or M) */
 int hnh_row_axpy_f64(double *D, const double *C, double alpha, const double *s,
                      const double *M, int64_t rows, int r, void *stream);
-/* elementwise vector helpers: out = (a + ca) / (b + cb) */
+/* elementwise vector helpers: out = (a + ca) / (b + cb); b == NULL: out = a + ca */
 int hnh_vec_quotient_f64(double *out, const double *a, double ca, const double *b, double cb,
                          int64_t n, void *stream);
 /* dst = alpha * x + beta * y elementwise (y may be NULL when beta == 0) */
