@@ -1,0 +1,154 @@
+"""ctypes front end of oracle/_ref/libhnh_ref.so -- TEST INFRASTRUCTURE.
+
+libhnh_ref.so is the REFERENCE's own code (PASSIONLab/distributed_sddmm, compiled unmodified
+from /root/reference by oracle/ref.mk) running with MPI ranks as threads on shimmed MPI / MKL /
+Eigen / CombBLAS.  It is the strongest checker this repo has: every distributed layout, block
+split, value order and ring data-flow in it is the reference's actual code.  Built only where
+/root/reference exists (this container); the built .so travels to the GPU box with the snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libhnh_ref.so")
+_LIB = None
+
+
+def available() -> bool:
+    return os.path.exists(SO)
+
+
+def build() -> bool:
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", _HERE, "-f", "ref.mk"], stdout=subprocess.DEVNULL)
+    return available()
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(SO)
+        P = C.c_void_p
+        L.ref_run.restype = P
+        L.ref_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P, P,
+                              C.c_char_p, C.c_int]
+        L.ref_error.restype = C.c_char_p
+        L.ref_error.argtypes = [P]
+        L.ref_free.argtypes = [P]
+        L.ref_rank_info.argtypes = [P, C.c_int, P]
+        for name in ("ref_submatrices",):
+            getattr(L, name).restype = P
+            getattr(L, name).argtypes = [P, C.c_int, C.c_int]
+        L.ref_num_values.restype = C.c_int64
+        L.ref_num_values.argtypes = [P, C.c_int, C.c_int]
+        for name in ("ref_value_rows", "ref_value_cols"):
+            getattr(L, name).restype = P
+            getattr(L, name).argtypes = [P, C.c_int, C.c_int]
+        L.ref_block_meta.argtypes = [P, C.c_int, C.c_int, C.c_int, P]
+        for name in ("ref_block_rowStart", "ref_block_col_idx", "ref_block_row_idx", "ref_block_values"):
+            getattr(L, name).restype = P
+            getattr(L, name).argtypes = [P, C.c_int, C.c_int, C.c_int]
+        for name in ("ref_op_A", "ref_op_B", "ref_op_values"):
+            getattr(L, name).restype = P
+            getattr(L, name).argtypes = [P, C.c_int, C.c_int]
+        L.ref_op_num_values.restype = C.c_int64
+        L.ref_op_num_values.argtypes = [P, C.c_int, C.c_int]
+        L.ref_op_elapsed.restype = C.c_double
+        L.ref_op_elapsed.argtypes = [P, C.c_int, C.c_int]
+        L.ref_benchmark.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                    C.c_char_p, C.c_char_p, C.c_int]
+        L.ref_benchmark.restype = None
+        _LIB = L
+    return _LIB
+
+
+def _arr(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double if dtype == np.float64 else
+                                                         C.c_int64 if dtype == np.int64 else C.c_int32)),
+                                 shape=(n,)).copy()
+
+
+def run(alg: str, p: int, c: int, R: int, M: int, N: int, rows, cols, vals, A, B, script, threads_per_rank: int = 1):
+    """Run `script` (list of ops) of the reference's `alg` on p thread-ranks.  rows/cols/vals must be
+    sorted by (row, col).  Returns a list (one per rank) of dicts with the layout, the local CSR
+    blocks, the global coordinates of every local value slot and the per-op local outputs."""
+    L = lib()
+    rows = np.ascontiguousarray(rows, np.uint64)
+    cols = np.ascontiguousarray(cols, np.uint64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    A = np.ascontiguousarray(A, np.float64)
+    B = np.ascontiguousarray(B, np.float64)
+    h = L.ref_run(alg.encode(), p, c, R, M, N, len(rows), rows.ctypes.data, cols.ctypes.data, vals.ctypes.data,
+                  A.ctypes.data, B.ctypes.data, ",".join(script).encode(), threads_per_rank)
+    try:
+        err = L.ref_error(h).decode()
+        if err:
+            raise RuntimeError(err)
+        out = []
+        for rank in range(p):
+            info = (C.c_int * 11)()
+            L.ref_rank_info(h, rank, info)
+            i, j, k, lAr, lAc, lBr, lBc, na, nb, nsb, nstb = list(info)
+            d = dict(i=i, j=j, k=k, localArows=lAr, localAcols=lAc, localBrows=lBr, localBcols=lBc)
+            d["aSubmatrices"] = _arr(L.ref_submatrices(h, rank, 0), 4 * na, np.int32).reshape(na, 4)
+            d["bSubmatrices"] = _arr(L.ref_submatrices(h, rank, 1), 4 * nb, np.int32).reshape(nb, 4)
+            for w, key, nblk in ((0, "S", nsb), (1, "ST", nstb)):
+                n = L.ref_num_values(h, rank, w)
+                d[key + "_rows"] = _arr(L.ref_value_rows(h, rank, w), n, np.int64)
+                d[key + "_cols"] = _arr(L.ref_value_cols(h, rank, w), n, np.int64)
+                blocks = []
+                for b in range(nblk):
+                    meta = (C.c_int64 * 5)()
+                    L.ref_block_meta(h, rank, w, b, meta)
+                    if meta[0]:
+                        blocks.append(None)
+                        continue
+                    nr, nc, nnz, tr = meta[1], meta[2], meta[3], meta[4]
+                    blocks.append(dict(rows=nr, cols=nc, transpose=bool(tr),
+                                       rowStart=_arr(L.ref_block_rowStart(h, rank, w, b), nr + 1, np.int64),
+                                       col_idx=_arr(L.ref_block_col_idx(h, rank, w, b), nnz, np.int64),
+                                       row_idx=_arr(L.ref_block_row_idx(h, rank, w, b), nnz, np.int64),
+                                       values=_arr(L.ref_block_values(h, rank, w, b), nnz, np.float64)))
+                d[key + "_blocks"] = blocks
+            ops = []
+            for t, name in enumerate(script):
+                nv = L.ref_op_num_values(h, rank, t)
+                ops.append(dict(op=name, A=_arr(L.ref_op_A(h, rank, t), lAr * lAc, np.float64).reshape(lAr, lAc),
+                                B=_arr(L.ref_op_B(h, rank, t), lBr * lBc, np.float64).reshape(lBr, lBc),
+                                values=_arr(L.ref_op_values(h, rank, t), nv, np.float64),
+                                elapsed=L.ref_op_elapsed(h, rank, t)))
+            d["ops"] = ops
+            out.append(d)
+        return out
+    finally:
+        L.ref_free(h)
+
+
+def assemble_dense(ranks, which: str, op_index: int, rows: int, R: int):
+    """Global matrix from the per-rank local outputs via the submatrix descriptors (replicas agree)."""
+    G = np.zeros((rows, R))
+    for d in ranks:
+        loc = d["ops"][op_index][which]
+        subs = d["aSubmatrices" if which == "A" else "bSubmatrices"]
+        at = 0
+        flat = loc.reshape(-1)
+        for top, left, nr, nc in subs:
+            blk = flat[at:at + nr * nc].reshape(nr, nc)
+            at += nr * nc
+            r_hi = min(top + nr, rows)
+            if r_hi > top:
+                G[top:r_hi, left:left + nc] = blk[:r_hi - top]
+    return G
+
+
+def benchmark(alg, p, c, R, logM, nnz_per_row, seed, fused=True, app="vanilla", output_file="/tmp/ref_bench.json",
+              threads_per_rank=1):
+    lib().ref_benchmark(alg.encode(), p, c, R, logM, nnz_per_row, seed, int(fused), app.encode(),
+                        output_file.encode(), threads_per_rank)

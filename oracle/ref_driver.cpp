@@ -1,0 +1,274 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE.  Builds oracle/_ref/libhnh_ref.so: the REFERENCE's
+// own sources (included from /root/reference, never copied) compiled UNMODIFIED against the
+// shims in oracle/shims/ (MPI ranks as threads, MKL inspector-executor restatement, mini Eigen,
+// CombBLAS stubs), plus a C entry point that runs the reference's algorithm classes on caller
+// inputs with p thread-ranks and hands back per-rank results.  What is the reference's own code
+// here: the SDDMM loop, every 1.5D / 2.5D algorithm, redistribution, block splitting, value
+// plumbing, benchmark_algorithm and the ALS application.  What is restated (shims): MKL's
+// COO->CSR + SpMM, MPI, Eigen, CombBLAS' generator.
+#include <mpi.h>
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// the reference, from where it lies
+#include "15D_dense_shift.hpp"
+#include "15D_sparse_shift.hpp"
+#include "25D_cannon_dense.hpp"
+#include "25D_cannon_sparse.hpp"
+#include "SpmatLocal.hpp"
+#include "benchmark_dist.hpp"
+#include "common.h"
+#include "distributed_sparse.h"
+#include "sparse_kernels.h"
+
+uint64_t hnh_shim_er_seed = 0xC0FFEEull;
+
+namespace {
+
+struct BlockDump {
+    bool is_null = true;
+    long rows = 0, cols = 0, nnz = 0;
+    int transpose = 0;
+    std::vector<int64_t> rowStart, col_idx, row_idx;
+    std::vector<double> values;
+};
+
+struct RankOut {
+    int i = 0, j = 0, k = 0;
+    int localArows = 0, localAcols = 0, localBrows = 0, localBcols = 0;
+    std::vector<int> asub, bsub;  // 4 ints per submatrix
+    std::vector<BlockDump> s_blocks, st_blocks;
+    std::vector<int64_t> s_row, s_col, st_row, st_col;  // global coordinate of every local value slot
+    // per op in the script
+    std::vector<std::vector<double>> A_out, B_out, val_out;
+    std::vector<double> elapsed;
+};
+
+struct Job {
+    std::string alg;
+    int p, c, R;
+    int64_t M, N, nnz;
+    const uint64_t *rows, *cols;
+    const double *vals;  // aligned with (rows, cols), which are sorted by (row, col)
+    const double *A, *B;  // global M x R, N x R
+    std::vector<std::string> script;
+    std::vector<RankOut> out;
+    std::string error;
+    std::mutex mu;
+};
+
+Distributed_Sparse *make_alg(const std::string &name, SpmatLocal *S, int R, int c, KernelImplementation *k) {
+    if (name == "15d_fusion1") return new Sparse15D_Dense_Shift(S, R, c, 1, k);
+    if (name == "15d_fusion2") return new Sparse15D_Dense_Shift(S, R, c, 2, k);
+    if (name == "15d_sparse") return new Sparse15D_Sparse_Shift(S, R, c, k);
+    if (name == "25d_dense_replicate") return new Sparse25D_Cannon_Dense(S, R, c, k);
+    if (name == "25d_sparse_replicate") return new Sparse25D_Cannon_Sparse(S, R, c, k);
+    return nullptr;
+}
+
+void dump_blocks(SpmatLocal &m, std::vector<BlockDump> &out) {
+    for (size_t b = 0; b < m.csr_blocks.size(); b++) {
+        BlockDump d;
+        CSRLocal *blk = m.csr_blocks[b];
+        if (blk) {
+            d.is_null = false;
+            d.rows = blk->rows; d.cols = blk->cols; d.nnz = blk->num_coords; d.transpose = blk->transpose;
+            CSRHandle *h = blk->getActive();
+            d.rowStart.assign(h->rowStart.begin(), h->rowStart.begin() + blk->rows + 1);
+            d.col_idx.assign(h->col_idx.begin(), h->col_idx.begin() + blk->num_coords);
+            d.row_idx.assign(h->row_idx.begin(), h->row_idx.begin() + blk->num_coords);
+            d.values.assign(h->values.begin(), h->values.begin() + blk->num_coords);
+        }
+        out.push_back(std::move(d));
+    }
+}
+
+// local dense matrix <- global matrix, via the submatrix descriptors (the layout dummyInitialize uses)
+void gather_local(DenseMatrix &loc, const std::vector<DenseSubmatrix> &subs, const double *global, int64_t grows, int R) {
+    double *p = loc.data();
+    for (const DenseSubmatrix &s : subs)
+        for (int i = 0; i < s.rowCount; i++)
+            for (int j = 0; j < s.colCount; j++) {
+                const int64_t gr = s.topRow + i, gc = s.leftCol + j;
+                *p++ = (gr < grows && gc < R) ? global[gr * R + gc] : 0.0;  // padded trailing blocks
+            }
+}
+std::vector<double> flatten(DenseMatrix &m) { return std::vector<double>(m.data(), m.data() + m.size()); }
+
+// global coordinate of each local value slot, recovered through the public API: SDDMM with
+// A = [row index, 0...], B = [1, 0...] gives the row; A = [1,0..], B = [col index, 0..] the column.
+void recover_coords(Distributed_Sparse *d, bool a_mode, std::vector<int64_t> &gr, std::vector<int64_t> &gc) {
+    DenseMatrix A = d->like_A_matrix(0.0), B = d->like_B_matrix(0.0);
+    VectorXd ones = a_mode ? d->like_S_values(1.0) : d->like_ST_values(1.0);
+    VectorXd res = a_mode ? d->like_S_values(0.0) : d->like_ST_values(0.0);
+    const KernelMode km = a_mode ? k_sddmmA : k_sddmmB;
+    for (int pass = 0; pass < 2; pass++) {
+        // first global column carries the index or a one; every other column is zero
+        auto fill = [&](DenseMatrix &X, const std::vector<DenseSubmatrix> &subs, bool index) {
+            double *p = X.data();
+            for (const DenseSubmatrix &s : subs)
+                for (int i = 0; i < s.rowCount; i++)
+                    for (int j = 0; j < s.colCount; j++) *p++ = (s.leftCol + j == 0) ? (index ? (double)(s.topRow + i) : 1.0) : 0.0;
+        };
+        fill(A, d->aSubmatrices, pass == 0);
+        fill(B, d->bSubmatrices, pass == 1);
+        d->initial_shift(&A, &B, km);
+        if (a_mode) d->sddmmA(A, B, ones, res); else d->sddmmB(A, B, ones, res);
+        d->de_shift(&A, &B, km);
+        std::vector<int64_t> &dst = pass == 0 ? gr : gc;
+        dst.resize((size_t)res.size());
+        for (long t = 0; t < res.size(); t++) dst[(size_t)t] = (int64_t)(res[t] + 0.5);
+    }
+}
+
+double lookup(const Job &J, int64_t r, int64_t c) {
+    // binary search in the (row, col)-sorted global tuple list
+    int64_t lo = 0, hi = J.nnz;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) / 2;
+        if ((int64_t)J.rows[mid] < r || ((int64_t)J.rows[mid] == r && (int64_t)J.cols[mid] < c)) lo = mid + 1; else hi = mid;
+    }
+    if (lo < J.nnz && (int64_t)J.rows[lo] == r && (int64_t)J.cols[lo] == c) return J.vals[lo];
+    return 0.0;
+}
+
+void rank_main(int rank, void *arg) {
+    Job &J = *(Job *)arg;
+    initialize_mpi_datatypes();
+    RankOut &O = J.out[(size_t)rank];
+    // this rank's share of the input tuples: a contiguous slice (any distribution is legal input)
+    SpmatLocal S;
+    const int64_t per = (J.nnz + J.p - 1) / J.p, lo = std::min<int64_t>(per * rank, J.nnz), hi = std::min<int64_t>(lo + per, J.nnz);
+    S.coords.resize((size_t)(hi - lo));
+    for (int64_t t = lo; t < hi; t++) S.coords[(size_t)(t - lo)] = spcoord_t{J.rows[t], J.cols[t], J.vals[t]};
+    S.M = (uint64_t)J.M; S.N = (uint64_t)J.N; S.dist_nnz = (uint64_t)J.nnz; S.initialized = true;
+
+    StandardKernel kernel;
+    Distributed_Sparse *d = make_alg(J.alg, &S, J.R, J.c, &kernel);
+    if (!d) { std::lock_guard<std::mutex> lk(J.mu); J.error = "unknown algorithm " + J.alg; return; }
+    O.i = d->grid->i; O.j = d->grid->j; O.k = d->grid->k;
+    O.localArows = d->localArows; O.localAcols = d->localAcols; O.localBrows = d->localBrows; O.localBcols = d->localBcols;
+    for (auto &s : d->aSubmatrices) { O.asub.push_back(s.topRow); O.asub.push_back(s.leftCol); O.asub.push_back(s.rowCount); O.asub.push_back(s.colCount); }
+    for (auto &s : d->bSubmatrices) { O.bsub.push_back(s.topRow); O.bsub.push_back(s.leftCol); O.bsub.push_back(s.rowCount); O.bsub.push_back(s.colCount); }
+    dump_blocks(*d->S, O.s_blocks);
+    dump_blocks(*d->ST, O.st_blocks);
+    recover_coords(d, true, O.s_row, O.s_col);
+    recover_coords(d, false, O.st_row, O.st_col);
+
+    VectorXd Sv = d->like_S_values(0.0), STv = d->like_ST_values(0.0);
+    for (long t = 0; t < Sv.size(); t++) Sv[t] = lookup(J, O.s_row[(size_t)t], O.s_col[(size_t)t]);
+    for (long t = 0; t < STv.size(); t++) STv[t] = lookup(J, O.st_row[(size_t)t], O.st_col[(size_t)t]);
+
+    for (const std::string &op : J.script) {
+        DenseMatrix A = d->like_A_matrix(0.0), B = d->like_B_matrix(0.0);
+        gather_local(A, d->aSubmatrices, J.A, J.M, J.R);
+        gather_local(B, d->bSubmatrices, J.B, J.N, J.R);
+        VectorXd res_s = d->like_S_values(0.0), res_st = d->like_ST_values(0.0);
+        std::vector<double> vout;
+        MPI_Barrier(MPI_COMM_WORLD);
+        const double t0 = MPI_Wtime();
+        if (op == "sddmmA") { d->initial_shift(&A, &B, k_sddmmA); d->sddmmA(A, B, Sv, res_s); d->de_shift(&A, &B, k_sddmmA); vout.assign(res_s.data(), res_s.data() + res_s.size()); }
+        else if (op == "sddmmB") { d->initial_shift(&A, &B, k_sddmmB); d->sddmmB(A, B, STv, res_st); d->de_shift(&A, &B, k_sddmmB); vout.assign(res_st.data(), res_st.data() + res_st.size()); }
+        else if (op == "spmmA") { d->initial_shift(&A, &B, k_spmmA); d->spmmA(A, B, Sv); d->de_shift(&A, &B, k_spmmA); }
+        else if (op == "spmmB") { d->initial_shift(&A, &B, k_spmmB); d->spmmB(A, B, STv); d->de_shift(&A, &B, k_spmmB); }
+        else if (op == "fusedA") { d->initial_shift(&A, &B, k_sddmmA); d->fusedSpMM(A, B, Sv, res_s, Amat); d->de_shift(&A, &B, k_sddmmA); vout.assign(res_s.data(), res_s.data() + res_s.size()); }
+        else if (op == "fusedB") { d->initial_shift(&A, &B, k_sddmmB); d->fusedSpMM(A, B, STv, res_st, Bmat); d->de_shift(&A, &B, k_sddmmB); vout.assign(res_st.data(), res_st.data() + res_st.size()); }
+        else { std::lock_guard<std::mutex> lk(J.mu); J.error = "unknown op " + op; }
+        MPI_Barrier(MPI_COMM_WORLD);
+        O.elapsed.push_back(MPI_Wtime() - t0);
+        O.A_out.push_back(flatten(A));
+        O.B_out.push_back(flatten(B));
+        O.val_out.push_back(std::move(vout));
+    }
+    delete d;
+}
+
+}  // namespace
+
+struct ref_result {
+    Job job;
+};
+
+extern "C" {
+
+// Runs `script` (comma-separated ops: sddmmA,sddmmB,spmmA,spmmB,fusedA,fusedB) of the REFERENCE
+// implementation of `alg` with p thread-ranks.  rows/cols/vals: the global tuples sorted by
+// (row, col); A, B: global dense inputs.  Each op starts from fresh copies of A and B.
+ref_result *ref_run(const char *alg, int p, int c, int R, int64_t M, int64_t N, int64_t nnz, const uint64_t *rows,
+                    const uint64_t *cols, const double *vals, const double *A, const double *B, const char *script,
+                    int threads_per_rank) {
+    ref_result *res = new ref_result();
+    Job &J = res->job;
+    J.alg = alg; J.p = p; J.c = c; J.R = R; J.M = M; J.N = N; J.nnz = nnz;
+    J.rows = rows; J.cols = cols; J.vals = vals; J.A = A; J.B = B;
+    std::string s(script ? script : "");
+    size_t pos = 0;
+    while (pos <= s.size() && !s.empty()) {
+        size_t q = s.find(',', pos);
+        if (q == std::string::npos) q = s.size();
+        if (q > pos) J.script.push_back(s.substr(pos, q - pos));
+        pos = q + 1;
+    }
+    J.out.resize((size_t)p);
+    hmpi_run(p, threads_per_rank, rank_main, &J);
+    return res;
+}
+const char *ref_error(ref_result *r) { return r->job.error.c_str(); }
+void ref_free(ref_result *r) { delete r; }
+
+void ref_rank_info(ref_result *r, int rank, int *out11) {
+    RankOut &O = r->job.out[(size_t)rank];
+    int v[11] = {O.i, O.j, O.k, O.localArows, O.localAcols, O.localBrows, O.localBcols, (int)(O.asub.size() / 4),
+                 (int)(O.bsub.size() / 4), (int)O.s_blocks.size(), (int)O.st_blocks.size()};
+    std::memcpy(out11, v, sizeof v);
+}
+const int *ref_submatrices(ref_result *r, int rank, int which) {
+    RankOut &O = r->job.out[(size_t)rank];
+    return which == 0 ? O.asub.data() : O.bsub.data();
+}
+int64_t ref_num_values(ref_result *r, int rank, int which) {
+    RankOut &O = r->job.out[(size_t)rank];
+    return (int64_t)(which == 0 ? O.s_row.size() : O.st_row.size());
+}
+const int64_t *ref_value_rows(ref_result *r, int rank, int which) { RankOut &O = r->job.out[(size_t)rank]; return which == 0 ? O.s_row.data() : O.st_row.data(); }
+const int64_t *ref_value_cols(ref_result *r, int rank, int which) { RankOut &O = r->job.out[(size_t)rank]; return which == 0 ? O.s_col.data() : O.st_col.data(); }
+// block meta: is_null, rows, cols, nnz, transpose
+void ref_block_meta(ref_result *r, int rank, int which, int block, int64_t *out5) {
+    RankOut &O = r->job.out[(size_t)rank];
+    BlockDump &b = (which == 0 ? O.s_blocks : O.st_blocks)[(size_t)block];
+    out5[0] = b.is_null; out5[1] = b.rows; out5[2] = b.cols; out5[3] = b.nnz; out5[4] = b.transpose;
+}
+const int64_t *ref_block_rowStart(ref_result *r, int rank, int which, int block) { RankOut &O = r->job.out[(size_t)rank]; return (which == 0 ? O.s_blocks : O.st_blocks)[(size_t)block].rowStart.data(); }
+const int64_t *ref_block_col_idx(ref_result *r, int rank, int which, int block) { RankOut &O = r->job.out[(size_t)rank]; return (which == 0 ? O.s_blocks : O.st_blocks)[(size_t)block].col_idx.data(); }
+const int64_t *ref_block_row_idx(ref_result *r, int rank, int which, int block) { RankOut &O = r->job.out[(size_t)rank]; return (which == 0 ? O.s_blocks : O.st_blocks)[(size_t)block].row_idx.data(); }
+const double *ref_block_values(ref_result *r, int rank, int which, int block) { RankOut &O = r->job.out[(size_t)rank]; return (which == 0 ? O.s_blocks : O.st_blocks)[(size_t)block].values.data(); }
+// op outputs: local A (localArows x localAcols), local B, value vector (may be empty)
+const double *ref_op_A(ref_result *r, int rank, int op) { return r->job.out[(size_t)rank].A_out[(size_t)op].data(); }
+const double *ref_op_B(ref_result *r, int rank, int op) { return r->job.out[(size_t)rank].B_out[(size_t)op].data(); }
+int64_t ref_op_num_values(ref_result *r, int rank, int op) { return (int64_t)r->job.out[(size_t)rank].val_out[(size_t)op].size(); }
+const double *ref_op_values(ref_result *r, int rank, int op) { return r->job.out[(size_t)rank].val_out[(size_t)op].data(); }
+double ref_op_elapsed(ref_result *r, int rank, int op) { return r->job.out[(size_t)rank].elapsed[(size_t)op]; }
+
+// The reference's own benchmark entry point (benchmark_dist.cpp:26-167) on its own generator
+// path (SpmatLocal::loadTuples -> the CombBLAS stub): p thread-ranks, 5 trials, JSON record
+// appended to output_file exactly as bench_erdos_renyi.cpp would.
+struct BenchArgs { int logM, nnz_per_row, R, c, fused; const char *alg, *out, *app; };
+static void bench_main(int, void *arg) {
+    BenchArgs &a = *(BenchArgs *)arg;
+    initialize_mpi_datatypes();
+    SpmatLocal S;
+    S.loadTuples(false, a.logM, a.nnz_per_row, "");
+    benchmark_algorithm(&S, a.alg, a.out, a.fused != 0, a.R, a.c, a.app);
+}
+void ref_benchmark(const char *alg, int p, int c, int R, int logM, int nnz_per_row, uint64_t seed, int fused,
+                   const char *app, const char *output_file, int threads_per_rank) {
+    hnh_shim_er_seed = seed;
+    BenchArgs a{logM, nnz_per_row, R, c, fused, alg, output_file, app};
+    hmpi_run(p, threads_per_rank, bench_main, &a);
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""Launch tests/mp_worker.py on N processes and load what the ranks wrote; reference-side helpers."""
+import json
+import os
+import socket
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ALL_OPS = ["sddmmA", "spmmA", "spmmB", "fusedA", "sddmmB", "fusedB"]
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def run_cases(nproc, cases, transport, timeout=600):
+    """Returns {case name: [per-rank dict]}."""
+    with tempfile.TemporaryDirectory() as td:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+               "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+               os.path.join(ROOT, "tests", "mp_worker.py"), json.dumps(cases), td, transport]
+        env = dict(os.environ, OMP_NUM_THREADS="2")
+        p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, text=True)
+        if p.returncode != 0:
+            raise RuntimeError("worker failed:\n" + p.stdout[-6000:])
+        out = {}
+        for case in cases:
+            ranks = []
+            for r in range(nproc):
+                z = np.load(os.path.join(td, f"{case['name']}_rank{r}.npz"), allow_pickle=False)
+                ranks.append({k: z[k] for k in z.files})
+            out[case["name"]] = ranks
+        return out
+
+
+def case(alg, c, R, logM, npr, seed=0xC0FFEE + 1, script=ALL_OPS, name=None, load="tuples"):
+    return dict(name=name or f"{alg}_c{c}_R{R}_m{logM}", alg=alg, c=c, R=R, logM=logM, npr=npr, seed=seed,
+                script=list(script), load=load)
+
+
+def reference_for(case_, p):
+    """The REFERENCE's per-rank view of the same case (oracle/_ref, or the committed golden file)."""
+    from oracle import hnh_oracle as orc
+    from oracle import ref
+    from tests.mp_worker import global_inputs, sval
+    N = 1 << case_["logM"]
+    rows, cols, _ = orc.er_tuples(case_["logM"], case_["npr"], case_["seed"])
+    A, B = global_inputs(N, case_["R"], case_["seed"])
+    golden = os.path.join(ROOT, "tests", "golden", f"{case_['name']}_p{p}.npz")
+    if ref.available():
+        vals = np.ones(len(rows)) if case_.get("load") == "er" else sval(rows, cols)
+        ranks = ref.run(case_["alg"], p, case_["c"], case_["R"], N, N, rows, cols, vals, A, B, case_["script"])
+        return ranks, "oracle/_ref"
+    if os.path.exists(golden):
+        return load_golden(golden, p), "tests/golden"
+    return None, None
+
+
+def flatten_ref(ranks):
+    """ref.run output -> flat dict of arrays (the golden-file format)."""
+    flat = {}
+    for r, d in enumerate(ranks):
+        for k in ("i", "j", "k", "localArows", "localAcols", "localBrows", "localBcols"):
+            flat[f"r{r}_{k}"] = np.int64(d[k])
+        for k in ("aSubmatrices", "bSubmatrices", "S_rows", "S_cols", "ST_rows", "ST_cols"):
+            flat[f"r{r}_{k}"] = d[k]
+        for key in ("S", "ST"):
+            flat[f"r{r}_{key}_nblocks"] = np.int64(len(d[key + "_blocks"]))
+            for b, blk in enumerate(d[key + "_blocks"]):
+                flat[f"r{r}_{key}_b{b}_null"] = np.bool_(blk is None)
+                if blk is not None:
+                    for f in ("rows", "cols", "transpose", "rowStart", "col_idx", "row_idx", "values"):
+                        flat[f"r{r}_{key}_b{b}_{f}"] = np.asarray(blk[f])
+        flat[f"r{r}_nops"] = np.int64(len(d["ops"]))
+        for t, op in enumerate(d["ops"]):
+            flat[f"r{r}_op{t}_A"], flat[f"r{r}_op{t}_B"], flat[f"r{r}_op{t}_values"] = op["A"], op["B"], op["values"]
+    return flat
+
+
+def load_golden(path, p):
+    z = np.load(path, allow_pickle=False)
+    ranks = []
+    for r in range(p):
+        g = lambda k: z[f"r{r}_{k}"]
+        d = {k: int(g(k)) for k in ("i", "j", "k", "localArows", "localAcols", "localBrows", "localBcols")}
+        for k in ("aSubmatrices", "bSubmatrices", "S_rows", "S_cols", "ST_rows", "ST_cols"):
+            d[k] = g(k)
+        for key in ("S", "ST"):
+            blocks = []
+            for b in range(int(g(key + "_nblocks"))):
+                if bool(g(f"{key}_b{b}_null")):
+                    blocks.append(None)
+                else:
+                    blocks.append({f: g(f"{key}_b{b}_{f}") for f in ("rows", "cols", "transpose", "rowStart", "col_idx", "row_idx", "values")})
+            d[key + "_blocks"] = blocks
+        d["ops"] = [dict(A=g(f"op{t}_A"), B=g(f"op{t}_B"), values=g(f"op{t}_values")) for t in range(int(g("nops")))]
+        ranks.append(d)
+    return ranks
+
+
+def compare_layout(got, want, alg):
+    """Index / layout parity: bit-exact."""
+    for r, (g, w) in enumerate(zip(got, want)):
+        for k in ("i", "j", "k", "localArows", "localAcols", "localBrows", "localBcols"):
+            assert int(g[k]) == int(w[k]), (r, k, int(g[k]), int(w[k]))
+        assert np.array_equal(g["aSubmatrices"], w["aSubmatrices"]), (r, "aSubmatrices")
+        assert np.array_equal(g["bSubmatrices"], w["bSubmatrices"]), (r, "bSubmatrices")
+        for key in ("S", "ST"):
+            wb = w[key + "_blocks"]
+            assert int(g[key + "_nblocks"]) == len(wb), (r, key, "block count")
+            for b, blk in enumerate(wb):
+                assert bool(g[f"{key}_b{b}_null"]) == (blk is None), (r, key, b, "null-ness")
+                if blk is None:
+                    continue
+                assert int(g[f"{key}_b{b}_rows"]) == int(blk["rows"]) and bool(g[f"{key}_b{b}_transpose"]) == bool(blk["transpose"])
+                if alg != "15d_sparse":  # the reference declares too few columns there (15D_sparse_shift.hpp:132)
+                    assert int(g[f"{key}_b{b}_cols"]) == int(blk["cols"])
+                for f in ("rowStart", "col_idx", "row_idx", "values"):
+                    assert np.array_equal(g[f"{key}_b{b}_{f}"], blk[f]), (r, key, b, f)
+
+
+def compare_ops(got, want, script, rtol=1e-11):
+    worst = 0.0
+    for r, (g, w) in enumerate(zip(got, want)):
+        for key in ("S_rows", "S_cols", "ST_rows", "ST_cols"):
+            assert np.array_equal(g[key], w[key]), (r, key)  # order of the local value vectors: bit-exact
+        for t, op in enumerate(script):
+            for f in ("A", "B", "values"):
+                a, b = g[f"op{t}_{f}"], w["ops"][t][f]
+                assert a.shape == b.shape, (r, op, f, a.shape, b.shape)
+                if a.size:
+                    err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+                    worst = max(worst, err)
+                    assert err < rtol, (r, op, f, err)
+    return worst

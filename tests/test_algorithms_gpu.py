@@ -1,0 +1,138 @@
+"""The distributed algorithm classes at p = 1 on the GPU, through the driver C ABI, against the
+global scipy/numpy reference (second oracle) and the dummyInitialize closed form.
+Multi-rank parity lives in tests/test_multirank_gpu.py."""
+import numpy as np
+import pytest
+
+from distributed_sddmm_b200 import driver as D
+from oracle import hnh_oracle as orc
+
+pytestmark = pytest.mark.gpu
+SEED = 0xC0FFEE + 3
+ALGS = ["15d_fusion1", "15d_fusion2", "15d_sparse", "25d_dense_replicate", "25d_sparse_replicate"]
+RTOL = 1e-11
+
+
+def rel_err(got, ref):
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def world():
+    D.world_init("self")
+    yield
+    D.world_finalize()
+
+
+@pytest.fixture(scope="module")
+def problem():
+    logM, npr, R = 10, 8, 32
+    N = 1 << logM
+    rows, cols, vals = orc.er_tuples(logM, npr, SEED)
+    rng = np.random.default_rng(17)
+    A = rng.uniform(-1, 1, (N, R))
+    B = rng.uniform(-1, 1, (N, R))
+    sv = rng.uniform(0.5, 1.5, len(rows))  # values in CSR order of S (row asc, col asc)
+    S, sddmm, spmmA, spmmB, fused = orc.global_reference(rows, cols, sv, A, B)
+    # the same nonzeros in CSR order of S^T
+    order_t = np.lexsort((rows, cols))
+    return dict(logM=logM, npr=npr, R=R, N=N, A=A, B=B, sv=sv, sv_t=sv[order_t], sddmm=sddmm, sddmm_t=sddmm[order_t],
+                spmmA=spmmA, spmmB=spmmB, fused=fused, S=S)
+
+
+@pytest.mark.parametrize("name", ALGS)
+def test_p1_operations_match_global_reference(world, problem, name):
+    P = problem
+    S = D.SpmatLocal.load_er(P["logM"], P["npr"], SEED)
+    alg = D.Algorithm(name, S, P["R"], 1)
+    A, B = alg.like_A_matrix(), alg.like_B_matrix()
+    Sv, res = alg.like_S_values(1.0), alg.like_S_values(0.0)
+    STv, res_t = alg.like_ST_values(1.0), alg.like_ST_values(0.0)
+    Sv.from_host(P["sv"])
+    STv.from_host(P["sv_t"])
+
+    def load():
+        A.from_host(P["A"])
+        B.from_host(P["B"])
+
+    # sddmmA: result = SValues o (A B^T sampled at S), in S's CSR order
+    load()
+    alg.initial_shift(A, B, "sddmmA")
+    alg.sddmmA(A, B, Sv, res)
+    alg.de_shift(A, B, "sddmmA")
+    assert rel_err(res.to_host(), P["sddmm"]) < RTOL
+    assert np.array_equal(A.to_host(), P["A"]) and np.array_equal(B.to_host(), P["B"])  # inputs untouched
+    # sddmmB: the same numbers in S^T's order
+    alg.initial_shift(A, B, "sddmmB")
+    alg.sddmmB(A, B, STv, res_t)
+    alg.de_shift(A, B, "sddmmB")
+    assert rel_err(res_t.to_host(), P["sddmm_t"]) < RTOL
+    # spmmA: A = S B (A's previous content is discarded)
+    alg.initial_shift(A, B, "spmmA")
+    alg.spmmA(A, B, Sv)
+    alg.de_shift(A, B, "spmmA")
+    assert rel_err(A.to_host(), P["spmmA"]) < RTOL
+    # spmmB: B = S^T A
+    load()
+    alg.initial_shift(A, B, "spmmB")
+    alg.spmmB(A, B, STv)
+    alg.de_shift(A, B, "spmmB")
+    assert rel_err(B.to_host(), P["spmmB"]) < RTOL
+    # fusedSpMM(Amat): A = (SDDMM values) B
+    load()
+    alg.initial_shift(A, B, "sddmmA")
+    alg.fusedSpMM(A, B, Sv, res, "A")
+    alg.de_shift(A, B, "sddmmA")
+    if name == "15d_fusion2":
+        # local kernel fusion treats S as an all-ones pattern and leaves sddmm_buffer unfilled
+        # (reference 15D_dense_shift.hpp:189,250-251)
+        ones = np.ones(len(P["sv"]))
+        _, _, _, _, fused1 = orc.global_reference(*_tuples(P), ones, P["A"], P["B"])
+        assert rel_err(A.to_host(), fused1) < RTOL
+    else:
+        assert rel_err(A.to_host(), P["fused"]) < RTOL
+        assert rel_err(res.to_host(), P["sddmm"]) < RTOL
+    assert np.array_equal(B.to_host(), P["B"])
+
+
+def _tuples(P):
+    S = P["S"]
+    rows = np.repeat(np.arange(P["N"]), np.diff(S.indptr)).astype(np.uint64)
+    return rows, S.indices.astype(np.uint64)
+
+
+@pytest.mark.parametrize("name", ALGS)
+def test_p1_dummy_initialize_closed_form(world, name):
+    """verify_operation of the reference (scratch.cpp:26-76) with a known answer: S == 1,
+    X[i,k] = i*R + k  =>  SDDMM(i,j) has a closed form that is exact in fp64."""
+    logM, npr, R = 12, 8, 16
+    rows, cols, vals = orc.er_tuples(logM, npr, SEED)
+    S = D.SpmatLocal.load_er(logM, npr, SEED)
+    alg = D.Algorithm(name, S, R, 1)
+    A, B = alg.like_A_matrix(), alg.like_B_matrix()
+    alg.dummyInitialize(A, "A")
+    alg.dummyInitialize(B, "B")
+    Sv, res = alg.like_S_values(1.0), alg.like_S_values(0.0)
+    alg.initial_shift(A, B, "sddmmA")
+    alg.sddmmA(A, B, Sv, res)
+    expect = orc.dummy_sddmm_closed_form(rows.astype(np.int64), cols.astype(np.int64), R)
+    assert np.array_equal(res.to_host(), expect)
+
+
+def test_benchmark_algorithm_record(world):
+    S = D.SpmatLocal.load_er(12, 8, SEED)
+    for name in ("15d_fusion1", "15d_fusion2"):
+        rec = D.benchmark_algorithm(S, name, R=32, c=1, fused=True, trials=3, warmup=1)
+        assert rec["alg_name"] == name and rec["num_trials"] == 3 and rec["fused"] is True
+        assert rec["overall_throughput"] > 0 and rec["elapsed"] > 0
+        assert rec["alg_info"]["nnz"] == S.info()["dist_nnz"]
+        assert set(rec["perf_stats"]) == {"Replication Time", "Cyclic Shift Time", "Computation Time"}
+
+
+def test_als_cg_reduces_residual(world):
+    """One ALS step on an artificial rank-R ground truth must not blow up and should shrink the residual."""
+    import ctypes as C
+    from distributed_sddmm_b200 import lib
+    S = D.SpmatLocal.load_er(10, 8, SEED)
+    rec = D.benchmark_algorithm(S, "15d_fusion2", R=16, c=1, fused=True, app="als", trials=1, warmup=0)
+    assert rec["overall_throughput"] > 0

@@ -1,0 +1,38 @@
+"""World size 2 and 4 on CPU (torch.distributed gloo through the External transport): the whole
+host-side setup path of every algorithm -- tuple generation per rank, redistribute_nonzeros,
+block splitting, CSR construction, the 2.5D setup skew -- against the REFERENCE's own code
+(oracle/_ref: reference sources compiled with shims, MPI ranks as threads), rank by rank and
+bit-exact.  BASELINE.json config 1 (N=2^14, 8 nnz/row, R=16, 1.5D sparse shift, world size 2)
+is the first case."""
+import pytest
+
+from tests import mp_util as U
+
+CASES_2 = [
+    U.case("15d_sparse", 1, 16, 14, 8, name="cfg1_15d_sparse", load="er"),
+    U.case("15d_fusion1", 1, 8, 7, 5),
+    U.case("15d_fusion2", 2, 8, 7, 5),
+    U.case("15d_sparse", 2, 8, 7, 5),
+    U.case("25d_sparse_replicate", 2, 8, 7, 5),
+]
+CASES_4 = [
+    U.case("15d_fusion1", 2, 8, 7, 5),
+    U.case("15d_sparse", 1, 8, 7, 5),
+    U.case("25d_dense_replicate", 1, 8, 7, 5),
+    U.case("25d_sparse_replicate", 1, 8, 7, 5),
+]
+
+
+@pytest.mark.parametrize("nproc,cases", [(2, CASES_2), (4, CASES_4)])
+def test_setup_path_matches_reference_rank_by_rank(nproc, cases):
+    cases = [dict(c, script=[]) for c in cases]
+    got = U.run_cases(nproc, cases, "gloo")
+    checked = 0
+    for c in cases:
+        want, src = U.reference_for(dict(c, script=[]), nproc)
+        if want is None:
+            continue
+        U.compare_layout(got[c["name"]], want, c["alg"])
+        checked += 1
+    if checked == 0:
+        pytest.skip("neither oracle/_ref nor golden files available")
