@@ -5,22 +5,26 @@ Contract (driver): `python bench.py --gpus N --steps K --warmup W` (N>1 launched
 torch.distributed.run, one rank per GPU) prints ONE JSON line on rank 0.
 
 * workload  : BASELINE.json configs[1] -- Erdos-Renyi N=2^20, 32 nnz/row, r=128, 1.5D
-              dense-shift FusedMM (`fusedSpMM(A, B, S, result, Amat)`,
-              reference benchmark_dist.cpp:117-141; A=B=0.001, S=1.0, :102-106).
-* step      : one fusedSpMM call over the whole distributed matrix.
+              dense-shift FusedMM: `fusedSpMM(A, B, S, result, Amat)` of
+              Sparse15D_Dense_Shift, exactly what bench_erdos_renyi / benchmark_algorithm time
+              (reference benchmark_dist.cpp:117-141; A=B=0.001, S=1.0, :102-106).  The C++ host
+              classes of libhnh_b200.so run it; this file only drives them (ctypes) and measures.
+* step      : one fusedSpMM call over the whole distributed matrix (strong scaling: the matrix
+              is fixed, N GPUs share it).
 * metric    : SDDMM+SpMM GFLOP/s with the reference's FLOP model 2*nnz*2*R per FusedMM
               (benchmark_dist.cpp:147).
-* value     : inputs resident in HBM.   e2e: host buffers, H2D/D2H inside the timed region.
-* roofline  : dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
-* cpu_baseline / --impl reference : the CPU oracle (restatement of the reference's
-              OpenMP SDDMM loop + CSR SpMM; MKL/MPI are not in the image) on the host cores.
+* value     : inputs resident in HBM.   e2e: per-rank pinned host buffers, H2D/D2H inside the
+              timed region.
+* roofline  : local kernels' algorithmic bytes / their CUDA-event time vs MEASURED_PEAKS.json.
+* cpu_baseline / --impl reference : the REFERENCE's own code (oracle/_ref: its sources compiled
+              unmodified against MPI/MKL/Eigen/CombBLAS shims) on the host cores; falls back to
+              the C port of its kernels (oracle/hnh_oracle.c) where oracle/_ref is not built.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -33,6 +37,7 @@ if ROOT not in sys.path:
 
 SEED = 0xC0FFEE + 2  # config index 2
 FALLBACK_HBM_GBS = 6650.0
+METRIC = "SDDMM+SpMM GFLOP/s (FusedMM, 4*nnz*R flop)"
 
 
 # ------------------------------------------------------------------ helpers ---------------
@@ -47,7 +52,8 @@ def measured_peaks():
 
 
 def algorithmic_bytes(kind: str, nnz: int, m: int, r: int, beta0: bool = False) -> int:
-    """fp64 w=8, int64 x=8.  beta0 variants do not read the old output."""
+    """fp64 w=8, int64 x=8, one local kernel call on a block with nnz nonzeros and
+    m CSR rows.  beta0 variants do not read the old output / values."""
     w = x = 8
     if kind == "sddmm":
         return nnz * (r * w + x + (w if beta0 else 2 * w)) + (m + 1) * x + m * r * w
@@ -58,327 +64,302 @@ def algorithmic_bytes(kind: str, nnz: int, m: int, r: int, beta0: bool = False) 
     raise ValueError(kind)
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+def fusedmm_bytes_per_rank(alg: str, nnz_rank: float, rows_stationary: int, steps: int, r: int) -> float:
+    """Algorithmic HBM bytes one rank's local kernels move in one FusedMM (sum over ring steps).
+    fusion 2: `steps` fused kernels on blocks of nnz_rank/steps nonzeros and rows_stationary rows;
+    values written once, the accumulator written at step 0 and read+written afterwards.
+    fusion 1: an SDDMM pass and an SpMM pass over the same blocks + the Hadamard / setCSRValues
+    plumbing (3 + 2 value passes)."""
+    w = x = 8
+    m = rows_stationary
+    if alg == "15d_fusion2":
+        return nnz_rank * (r * w + x + w) + steps * ((m + 1) * x + m * r * w) + (2 * steps - 1) * m * r * w
+    sddmm = nnz_rank * (r * w + x + w) + steps * ((m + 1) * x + m * r * w)
+    spmm = nnz_rank * (r * w + x + w) + steps * ((m + 1) * x + 2 * m * r * w)
+    return sddmm + spmm + 5 * w * nnz_rank
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region (NVML, 5 ms period)."""
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.t = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                  "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": [self.err or "no samples"]}
+        self._stop.set()
+        self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
-def generate_er(L, logM, npr, seed, row_lo, row_hi):
-    cap = (row_hi - row_lo) * npr
-    r = np.empty(cap, np.uint64)
-    c = np.empty(cap, np.uint64)
-    v = np.empty(cap, np.float64)
-    n = L.hnh_er_generate_host(logM, npr, seed, row_lo, row_hi, r.ctypes.data, c.ctypes.data,
-                               v.ctypes.data, cap)
-    if n < 0:
-        raise RuntimeError(L.hnh_last_error_string().decode())
-    return r[:n], c[:n], v[:n]
-
-
-def build_csr(L, rows, cols, r, c, v, transpose=False):
-    nnz = len(r)
-    out_rows = cols if transpose else rows
-    rs = np.empty(out_rows + 1, np.int64)
-    ci = np.empty(max(nnz, 1), np.int64)
-    ri = np.empty(max(nnz, 1), np.int64)
-    vv = np.empty(max(nnz, 1), np.float64)
-    rc = L.hnh_coo_to_csr_host(rows, cols, nnz, r.ctypes.data, c.ctypes.data, v.ctypes.data,
-                               int(transpose), rs.ctypes.data, ci.ctypes.data, ri.ctypes.data,
-                               vv.ctypes.data)
-    if rc:
-        raise RuntimeError(L.hnh_last_error_string().decode())
-    return rs, ci[:nnz], ri[:nnz], vv[:nnz]
+def workload_config(args, where, **extra):
+    cfg = {"workload": f"Erdos-Renyi N=2^{args.logM} nnz/row={args.nnz_per_row} r={args.R} FusedMM "
+                       f"(Sparse15D_Dense_Shift::fusedSpMM, {args.alg})",
+           "logM": args.logM, "nnz_per_row": args.nnz_per_row, "R": args.R, "algorithm": args.alg, "c": args.c,
+           "seed": SEED, "index_type": "int64", "where": where,
+           "l2": "per-GPU working set (dense shards + CSR) exceeds the 126 MB L2 and every step gathers "
+                 "from a different block; no explicit flush between steps"}
+    cfg.update(extra)
+    return cfg
 
 
 # ------------------------------------------------------------------ CPU arm ---------------
-def cpu_fusedmm_sample(L, args, budget_s=12.0):
-    """Time the CPU oracle (reference restatement) on a bounded row-sample of the workload:
-    the first m_s rows of S against the full B -- per-row work is identical to the full job,
-    so GFLOP/s carries over.  Returns (gflops, cores, description)."""
+def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
+    """GFLOP/s of the reference's fusedSpMM on the host cores (rank 0 only).  Uses oracle/_ref
+    (the reference's own code) when built, else the C port of its kernels.  The sample is the
+    whole configured matrix when that fits the time budget, otherwise the same configuration at
+    a smaller logM (same nnz/row and r: identical per-nonzero work)."""
+    from oracle import ref
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        pass
+    if ref.available():
+        nnz0, s0 = ref.time_fused(args.alg, 1, 1, args.R, min(args.logM, 16), args.nnz_per_row, SEED, 1, 1, cores)
+        gf0 = 4.0 * nnz0 * args.R / s0[-1] / 1e9
+        logM = args.logM
+        while logM > 16:
+            flop = 4.0 * (1 << logM) * args.nnz_per_row * args.R
+            # fusedSpMM calls + construction (redistribution, sorts, two COO->CSR), ~6 call-equivalents
+            if (warmup + steps + 6) * flop / (gf0 * 1e9) <= budget_s:
+                break
+            logM -= 1
+        nnz, secs = ref.time_fused(args.alg, 1, 1, args.R, logM, args.nnz_per_row, SEED, warmup, steps, cores)
+        per = secs[warmup:]
+        gf = 4.0 * nnz * args.R / per / 1e9
+        desc = (f"the reference's own code (oracle/_ref: reference sources compiled unmodified; MKL/MPI/Eigen/"
+                f"CombBLAS shimmed) {args.alg} p=1, {cores} OpenMP threads, Erdos-Renyi N=2^{logM} "
+                f"nnz/row={args.nnz_per_row} r={args.R} (nnz={nnz}), {len(per)} fusedSpMM calls after {warmup} warm-up, "
+                f"{np.mean(per)*1e3:.1f} ms each")
+        return float(np.mean(gf)), cores, "reference", desc, float(np.mean(per)) * 1e3
+    # fall-back: C port of the two local kernels on a row sample
+    from distributed_sddmm_b200 import lib
     from oracle import hnh_oracle as orc
-    N = 1 << args.logM
-    R = args.R
-    rng_rows = min(N, 1 << 16)
-    r, c, v = generate_er(L, args.logM, args.nnz_per_row, SEED, 0, rng_rows)
-    A = np.full((N, R), 0.001)
-    B = np.full((N, R), 0.001)
-
-    def run(mrows, trials):
-        rr, cc, vv = (r, c, v) if mrows == rng_rows else generate_er(L, args.logM, args.nnz_per_row, SEED, 0, mrows)
-        rs, ci, ri, _ = build_csr(L, mrows, N, rr, cc, vv)
-        vals = np.zeros(len(ci))
-        out = np.zeros((mrows, R))
-        orc.fused_block(rs, ri, ci, vals, A[:mrows], B, out)  # warm-up
+    L = lib()
+    N, R = 1 << args.logM, args.R
+    mrows = min(N, 1 << 17)
+    cap = mrows * args.nnz_per_row
+    r = np.empty(cap, np.uint64); c = np.empty(cap, np.uint64); v = np.empty(cap, np.float64)
+    n = L.hnh_er_generate_host(args.logM, args.nnz_per_row, SEED, 0, mrows, r.ctypes.data, c.ctypes.data, v.ctypes.data, cap)
+    csr = orc.coo_to_csr(mrows, N, r[:n], c[:n], v[:n])
+    A = np.full((mrows, R), 0.001); B = np.full((N, R), 0.001)
+    vals = np.zeros(n); out = np.zeros((mrows, R))
+    ts = []
+    for i in range(warmup + steps):
+        vals[:] = 0; out[:] = 0
         t0 = time.perf_counter()
-        for _ in range(trials):
-            vals[:] = 0.0
-            out[:] = 0.0
-            orc.fused_block(rs, ri, ci, vals, A[:mrows], B, out)
-        dt = (time.perf_counter() - t0) / trials
-        return 4.0 * len(ci) * R / dt / 1e9, dt, len(ci)
-
-    g, dt, nnz = run(rng_rows, 1)
-    # scale the sample so that 3 trials take about budget_s
-    scale = max(1.0, min(N / rng_rows, budget_s / 3.0 / max(dt, 1e-6)))
-    mrows = int(min(N, rng_rows * scale))
-    mrows = max(rng_rows, (mrows >> 12) << 12)
-    if mrows > rng_rows:
-        g, dt, nnz = run(mrows, 3)
-    cores = orc.num_threads()
-    desc = (f"CPU restatement of reference (MKL/MPI unavailable in image): OpenMP SDDMM loop + CSR "
-            f"SpMM on the first {mrows} of {N} rows (nnz={nnz}) against the full B, "
-            f"{cores} threads, {dt*1e3:.1f} ms per FusedMM sample")
-    return g, cores, desc, dt, mrows, nnz
+        orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, vals, A, B, out)
+        ts.append(time.perf_counter() - t0)
+    per = np.array(ts[warmup:])
+    gf = 4.0 * n * R / per / 1e9
+    desc = (f"C port of the reference kernels (oracle/hnh_oracle.c; oracle/_ref not built), first {mrows} of {N} rows "
+            f"against the full B, {orc.num_threads()} threads")
+    return float(np.mean(gf)), orc.num_threads(), "port", desc, float(np.mean(per)) * 1e3
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    from distributed_sddmm_b200 import lib
-    L = lib()
-    # K steps of a bounded sample each; keep the whole run within a few minutes
-    per_step = max(1.0, min(12.0, 120.0 / max(1, args.steps + args.warmup)))
-    samples = []
-    desc = cores = None
-    for i in range(args.warmup + args.steps):
-        g, cores, desc, dt, mrows, nnz = cpu_fusedmm_sample(L, args, budget_s=per_step * 3)
-        if i >= args.warmup:
-            samples.append((g, dt))
-    g = float(np.mean([s[0] for s in samples]))
-    ms = float(np.mean([s[1] for s in samples])) * 1e3
+    steps, warmup = args.steps, min(args.warmup, 1)
+    # keep the whole run within a few minutes whatever K is: cap the number of timed calls
+    steps_run = min(steps, 5)
+    g, cores, kind, desc, ms = cpu_reference_fusedmm(args, warmup, steps_run, budget_s=90.0)
     line = {
-        "impl": "reference", "metric": "SDDMM+SpMM GFLOP/s (FusedMM, 4*nnz*R flop)", "value": g,
-        "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, "cpu"),
-        "cpu_baseline": {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc},
+        "impl": "reference", "metric": METRIC, "value": g, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, "cpu", steps_timed=steps_run),
+        "cpu_baseline": {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": g, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
 
 
-def workload_config(args, where):
-    return {"workload": f"Erdos-Renyi N=2^{args.logM} nnz/row={args.nnz_per_row} r={args.R} FusedMM "
-                        f"(fusedSpMM, 1.5D dense-shift, {args.alg})",
-            "logM": args.logM, "nnz_per_row": args.nnz_per_row, "R": args.R, "algorithm": args.alg,
-            "c": args.c, "seed": SEED, "index_type": "int64", "where": where,
-            "l2": "inputs (dense factors + CSR) are far larger than the 126 MB L2; no flush needed"}
-
-
 # ------------------------------------------------------------------ GPU arm ---------------
 def run_native(args):
     import torch
-    from distributed_sddmm_b200 import lib, check
+    from distributed_sddmm_b200 import driver as D
+    from distributed_sddmm_b200 import lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path "
-                         "(use --impl reference for the CPU arm)")
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     L = lib()
-    if world > 1:
-        from distributed_sddmm_b200 import dist_bench
-        return dist_bench.run(args)
+    rank, world = D.world_init()
+    import torch.distributed as dist
 
-    dev = torch.device("cuda", local_rank)
-    N, R = 1 << args.logM, args.R
-    r, c, v = generate_er(L, args.logM, args.nnz_per_row, SEED, 0, N)
-    rs, ci, ri, vals = build_csr(L, N, N, r, c, v)
-    nnz = len(ci)
-    del r, c, v
-    d_rs, d_ci = torch.from_numpy(rs).to(dev), torch.from_numpy(ci).to(dev)
-    d_vals = torch.zeros(nnz, dtype=torch.float64, device=dev)
-    d_S = torch.ones(nnz, dtype=torch.float64, device=dev)       # like_S_values(1.0)
-    d_res = torch.zeros(nnz, dtype=torch.float64, device=dev)    # sddmm_result
-    A = torch.full((N, R), 0.001, dtype=torch.float64, device=dev)  # like_A_matrix(0.001)
-    B = torch.full((N, R), 0.001, dtype=torch.float64, device=dev)
-    st = torch.cuda.current_stream().cuda_stream
-    BETA0 = 4
-    kev = []  # (start, end) events around the dominant kernel
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step_fusion2(record=False):
-        # Sparse15D_Dense_Shift::fusedSpMM, fusion 2, p = c = 1 (15D_dense_shift.hpp:151-252):
-        # values = 0; K1; K2 into the accumulator; A = accumulator -- one fused kernel, in place.
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        check(L.hnh_fused_f64(d_rs.data_ptr(), d_ci.data_ptr(), d_vals.data_ptr(), N, nnz,
-                              A.data_ptr(), B.data_ptr(), A.data_ptr(), R, BETA0, st), "fused")
-        if record:
-            e1.record()
-            kev.append((e0, e1))
+    def sync_barrier():
+        L.hnhd_device_synchronize()
+        if world > 1:
+            L.hnhd_barrier()
 
-    def step_fusion1(record=False):
-        # Distributed_Sparse::fusedSpMM (distributed_sparse.h:296-312) = sddmmA, A.setZero(),
-        # spmmA with the SDDMM result, p = c = 1.
-        check(L.hnh_sddmm_f64(d_rs.data_ptr(), d_ci.data_ptr(), d_vals.data_ptr(), N, nnz,
-                              A.data_ptr(), B.data_ptr(), R, BETA0, st), "sddmm")
-        check(L.hnh_hadamard_f64(d_res.data_ptr(), d_S.data_ptr(), d_vals.data_ptr(), nnz, st), "hadamard")
-        if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        check(L.hnh_spmm_f64(d_rs.data_ptr(), d_ci.data_ptr(), d_res.data_ptr(), N, nnz,
-                             B.data_ptr(), A.data_ptr(), R, BETA0, st), "spmm")
-        if record:
-            e1.record()
-            kev.append((e0, e1))
+    N, R, c = 1 << args.logM, args.R, args.c
+    S = D.SpmatLocal.load_er(args.logM, args.nnz_per_row, SEED)
+    nnz = S.info()["dist_nnz"]
+    alg = D.Algorithm(args.alg, S, R, c)
+    info = alg.info()
+    A, B = alg.like_A_matrix(0.001), alg.like_B_matrix(0.001)
+    Sv, res = alg.like_S_values(1.0), alg.like_S_values(0.0)
+    steps_ring = world // c
 
-    step = step_fusion2 if args.alg == "15d_fusion2" else step_fusion1
-    dominant = "fused" if args.alg == "15d_fusion2" else "spmm"
+    def step():
+        alg.fusedSpMM(A, B, Sv, res, "A")
 
-    def reset_inputs():
-        A.fill_(0.001)
-
-    def timed(fn, steps, warmup, record):
-        for _ in range(warmup):
-            reset_inputs()
-            fn(False)
-        torch.cuda.synchronize()
-        t = 0.0
-        for _ in range(steps):
-            reset_inputs()  # untimed: restore the benchmark inputs (A is overwritten by FusedMM)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn(record)
-            e1.record()
-            torch.cuda.synchronize()
-            t += e0.elapsed_time(e1)
-        return t / steps
-
+    for _ in range(args.warmup):
+        step()
+    sync_barrier()
+    alg.reset_timers()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = L.hnh_launch_count()
-    ms = timed(step, args.steps, args.warmup, True)
-    launches = (L.hnh_launch_count() - launches0)
+    sync_barrier()
+    D.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms_total = D.timer_stop()
+    sync_barrier()
+    launches = L.hnh_launch_count() - launches0
     clocks = sampler.stop()
-    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    ms = max_over_ranks(ms_total) / args.steps
     flops = 4.0 * nnz * R
     gflops = flops / (ms * 1e-3) / 1e9
+    perf = alg.perf()  # collective: averages over ranks
 
-    # dominant-kernel roofline
-    kms = float(np.mean([a.elapsed_time(b) for a, b in kev])) if kev else ms
-    bytes_alg = algorithmic_bytes(dominant, nnz, N, R, beta0=True)
+    # ---- roofline of the local kernels (dominant: the fused / SpMM kernel) ----
+    comp_ms = perf["Computation Time"] * 1e3 / args.steps
+    nnz_rank = float(np.mean(info["nnz_procs"]))
+    rows_stationary = alg.dims.localArows * c
+    bytes_rank = fusedmm_bytes_per_rank(args.alg, nnz_rank, rows_stationary, steps_ring, R)
     peak, peak_kind = measured_peaks()
-    achieved = bytes_alg / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": f"of {peak_kind}",
-                "kernel": f"{dominant}_row_kernel<{R}> (BETA0)", "kernel_ms": kms,
-                "algorithmic_bytes_per_launch": bytes_alg}
+    achieved = bytes_rank / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": f"of {peak_kind}",
+                "kernel": ("fused_row_kernel" if args.alg == "15d_fusion2" else "sddmm_row_kernel + spmm_row_kernel") +
+                          f"<{R}>, {steps_ring} launch(es) per step per GPU",
+                "kernel_ms_per_step": comp_ms, "algorithmic_bytes_per_step_per_gpu": bytes_rank}
     prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and world == 1:
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{dominant}_{R}")
-        except Exception:
+            roofline["traffic"] = json.load(open(prof)).get(f"{'fused' if args.alg == '15d_fusion2' else 'spmm'}_{R}")
+        except Exception:  # noqa: BLE001
             pass
+    shift_ms = perf.get("Cyclic Shift Time", 0.0) * 1e3 / args.steps
+    repl_ms = perf.get("Replication Time", 0.0) * 1e3 / args.steps
 
-    # the other variant, for the record (not the headline)
-    other_name = "15d_fusion1" if args.alg == "15d_fusion2" else "15d_fusion2"
-    other = step_fusion1 if args.alg == "15d_fusion2" else step_fusion2
-    oms = timed(other, max(3, args.steps // 2), 2, False)
+    # ---- the other fusion strategy, for the record (not the headline) ----
+    other = None
+    if world == 1 and not args.no_other:
+        oname = "15d_fusion1" if args.alg == "15d_fusion2" else "15d_fusion2"
+        oalg = D.Algorithm(oname, S, R, c)
+        oSv, ores = oalg.like_S_values(1.0), oalg.like_S_values(0.0)
+        for _ in range(2):
+            oalg.fusedSpMM(A, B, oSv, ores, "A")
+        sync_barrier()
+        D.timer_start()
+        for _ in range(max(3, args.steps // 2)):
+            oalg.fusedSpMM(A, B, oSv, ores, "A")
+        oms = D.timer_stop() / max(3, args.steps // 2)
+        other = {oname: {"ms_per_step": oms, "gflops": flops / (oms * 1e-3) / 1e9}}
+        del oalg, oSv, ores
 
-    # ---- e2e: host buffers through the C-ABI block API, copies inside the timed region ----
-    import ctypes as C
-    blk = C.c_void_p()
-    check(L.hnh_block_create_host(rs.ctypes.data, ci.ctypes.data, N, N, nnz, R, C.byref(blk)), "block_create")
-    hA = torch.full((N, R), 0.001, dtype=torch.float64).pin_memory()
-    hB = torch.full((N, R), 0.001, dtype=torch.float64).pin_memory()
-    hV = torch.zeros(nnz, dtype=torch.float64).pin_memory()
-    hO = torch.zeros((N, R), dtype=torch.float64).pin_memory()
+    # ---- e2e: per-rank pinned HOST buffers in, result out, copies inside the timed region ----
+    shapeA, shapeB = A.shape, B.shape
+    hA = torch.full(shapeA, 0.001, dtype=torch.float64).pin_memory()
+    hB = torch.full(shapeB, 0.001, dtype=torch.float64).pin_memory()
+    hO = torch.empty(shapeA, dtype=torch.float64).pin_memory()
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
-        check(L.hnh_block_run_host(blk, 2, hA.data_ptr(), hB.data_ptr(), hV.data_ptr(), hO.data_ptr(),
-                                   R, 3, st), "block_run_host")
+        D.check(L.hnhd_dense_from_host(A.h, hA.data_ptr()), "from_host")
+        D.check(L.hnhd_dense_from_host(B.h, hB.data_ptr()), "from_host")
+        alg.fusedSpMM(A, B, Sv, res, "A")
+        D.check(L.hnhd_dense_to_host(A.h, hO.data_ptr()), "to_host")
 
     e2e_step()
-    torch.cuda.synchronize()
+    sync_barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
-    L.hnh_block_destroy(blk)
-    h2d = 2 * N * R * 8
-    d2h = N * R * 8 + nnz * 8
+    sync_barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
+    h2d = (shapeA[0] * shapeA[1] + shapeB[0] * shapeB[1]) * 8 * world
+    d2h = shapeA[0] * shapeA[1] * 8 * world
     e2e = {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "api": "hnh_block_run_host(op=fused): pinned host A,B in; A result + SDDMM values out"}
-    del hA, hB, hV, hO
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "api": "per rank: DenseMatrix::copy_from_host(A), (B) from pinned memory; fusedSpMM; copy_to_host(A)"}
+    del hA, hB, hO
 
-    # ---- CPU baseline on the host cores (bounded sample) ----
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----
     cpu = None
-    if not args.no_cpu_baseline:
-        g, cores, desc, _, _, _ = cpu_fusedmm_sample(L, args)
-        cpu = {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": desc}
+    if world == 1 and not args.no_cpu_baseline:
+        g, cores, kind, desc, _ = cpu_reference_fusedmm(args, 1, 3)
+        cpu = {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc}
 
-    line = {
-        "metric": "SDDMM+SpMM GFLOP/s (FusedMM, 4*nnz*R flop)", "value": gflops, "unit": "GFLOP/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": dict(workload_config(args, "cuda"), nnz=nnz, p=1),
-        "hbm_gbs_achieved": (bytes_alg if args.alg == "15d_fusion2" else
-                             algorithmic_bytes("sddmm", nnz, N, R, True) + 3 * 8 * nnz +
-                             algorithmic_bytes("spmm", nnz, N, R, True)) / (ms * 1e-3) / 1e9,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed),
-        "clocks": clocks,
-        "other": {other_name: {"ms_per_step": oms, "gflops": flops / (oms * 1e-3) / 1e9}},
-    }
-    print(json.dumps(line))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, "cuda", nnz=nnz, p=world, transport=("nccl" if world > 1 else "self"),
+                                      ring_steps=steps_ring, local_rows=alg.dims.localArows),
+            "hbm_gbs_achieved_per_gpu": bytes_rank / (ms * 1e-3) / 1e9,
+            "roofline": roofline,
+            "phase_ms_per_step": {"computation": comp_ms, "cyclic_shift": shift_ms, "replication": repl_ms},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if other:
+            line["other"] = other
+        print(json.dumps(line))
+    del alg, S
+    D.world_finalize()
     return 0
 
 
@@ -391,15 +372,25 @@ def main():
     ap.add_argument("--logM", type=int, default=20)
     ap.add_argument("--nnz-per-row", type=int, default=32)
     ap.add_argument("--R", type=int, default=128)
-    ap.add_argument("--c", type=int, default=1)
+    ap.add_argument("--c", type=int, default=0, help="replication factor (0 = the tuned default for this GPU count)")
     ap.add_argument("--alg", default="15d_fusion2", choices=["15d_fusion1", "15d_fusion2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.c <= 0:
+        args.c = default_c(args.alg, world)
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_native(args)
+
+
+def default_c(alg: str, world: int) -> int:
+    """Replication factor per GPU count (measured sweep, profiles/r01_scaling.md)."""
+    table = {1: 1, 2: 1, 4: 1, 8: 1}
+    return table.get(world, 1)
 
 
 if __name__ == "__main__":

@@ -194,6 +194,10 @@ void DenseMatrix::copy_from_host(const double *h) {
     if (size()) cuda_check(cudaMemcpyAsync(data(), h, sizeof(double) * (size_t)size(), cudaMemcpyHostToDevice, cs()), "h2d");
     cuda_check(cudaStreamSynchronize(cs()), "sync");
 }
+void DenseMatrix::copy_to_host(double *h) const {
+    if (size()) cuda_check(cudaMemcpyAsync(h, data(), sizeof(double) * (size_t)size(), cudaMemcpyDeviceToHost, cs()), "d2h");
+    cuda_check(cudaStreamSynchronize(cs()), "sync");
+}
 vector<double> DenseMatrix::to_host() const { return buf_.to_host((size_t)size(), cs()); }
 
 VectorXd batch_dot_product(const DenseMatrix &A, const DenseMatrix &B) {

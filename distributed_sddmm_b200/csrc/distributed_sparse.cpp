@@ -194,3 +194,20 @@ void Distributed_Sparse::hadamard_values(VectorXd &result, VectorXd &SValues, Sp
             hnh::cuda_check(cudaMemsetAsync(result.data() + off, 0, sizeof(double) * (size_t)n, compute()), "memset");
     }
 }
+
+hnh::PeerRing *Distributed_Sparse::peer_ring(std::shared_ptr<hnh::Comm> world, size_t bytes) {
+    if (peer_ring_broken_ || !hnh::PeerRing::enabled() || world->size() < 2) return nullptr;
+    auto key = std::make_pair(world.get(), bytes);
+    auto it = peer_rings_.find(key);
+    if (it != peer_rings_.end()) return it->second.get();
+    try {
+        peer_rings_[key].reset(new hnh::PeerRing(world, bytes));
+    } catch (const hnh::Error &e) {
+        // peer mapping unavailable (e.g. no NVLink/IPC): the NCCL ring below does the same job
+        if (verbose) cout << "PeerRing unavailable, using NCCL send/recv: " << e.what() << endl;
+        peer_rings_.erase(key);
+        peer_ring_broken_ = true;
+        return nullptr;
+    }
+    return peer_rings_[key].get();
+}

@@ -215,10 +215,7 @@ int hnhd_dense_dummy_initialize(hnhd_alg_t *a, hnhd_dense_t *m, int which) {
 }
 int hnhd_dense_from_host(hnhd_dense_t *m, const double *host) { return guarded([&] { m->m.copy_from_host(host); }); }
 int hnhd_dense_to_host(const hnhd_dense_t *m, double *host) {
-    return guarded([&] {
-        vector<double> h = m->m.to_host();
-        std::memcpy(host, h.data(), sizeof(double) * h.size());
-    });
+    return guarded([&] { m->m.copy_to_host(host); });
 }
 int hnhd_dense_shape(const hnhd_dense_t *m, int64_t *rows, int64_t *cols) {
     *rows = m->m.rows();

@@ -129,7 +129,7 @@ public:
         // the riding matrix is written only by the fusion-1 SpMM (it is the output there)
         const bool riding_is_input = sddmm || fusionApproach == 2;
 
-        ring_dense(*riding, *grid->col_world, riding_is_input, "Cyclic Shift Time", "Computation Time",
+        ring_dense(*riding, grid->col_world, riding_is_input, "Cyclic Shift Time", "Computation Time",
                    [&](int step, DenseMatrix &shard) {
                        if (sk) sk->values_are_zero = sddmm;
                        kernel->triple_function(local_mode, *choice, fixed, shard, block_at(step), 0);
@@ -174,7 +174,7 @@ public:
             region_end("Computation Time", compute());
         }
 
-        ring_dense(*riding, *grid->col_world, true, "Cyclic Shift Time", "Computation Time",
+        ring_dense(*riding, grid->col_world, true, "Cyclic Shift Time", "Computation Time",
                    [&](int step, DenseMatrix &shard) {
                        kernel->fused_local(*choice, gathered, shard, out, block_at(step), sk != nullptr,
                                            sk != nullptr && step == 0);

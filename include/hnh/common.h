@@ -145,6 +145,7 @@ public:
     static DenseMatrix from_host(const double *h, int64_t rows, int64_t cols);
     vector<double> to_host() const;
     void copy_from_host(const double *h);
+    void copy_to_host(double *h) const;  // synchronises
     void swap(DenseMatrix &o) { buf_.swap(o.buf_); std::swap(rows_, o.rows_); std::swap(cols_, o.cols_); }
 
 private:

@@ -25,6 +25,7 @@
 #include "hnh/SpmatLocal.hpp"
 #include "hnh/common.h"
 #include "hnh/json.h"
+#include "hnh/peer_ring.h"
 #include "hnh/sparse_kernels.h"
 
 class DenseSubmatrix {
@@ -140,6 +141,11 @@ protected:
     // 15D_dense_shift.hpp:366, which allocates two temporaries and makes three extra passes)
     void hadamard_values(VectorXd &result, VectorXd &SValues, SpmatLocal &m);
 
+    // copy-engine rings (hnh/peer_ring.h), one per (ring communicator, shard size), built on first use
+    std::map<std::pair<hnh::Comm *, size_t>, std::unique_ptr<hnh::PeerRing>> peer_rings_;
+    bool peer_ring_broken_ = false;
+    hnh::PeerRing *peer_ring(std::shared_ptr<hnh::Comm> world, size_t bytes);
+
     // Driver of a dense ring over `world` (+1 direction, `steps` = world size):
     //   step t: body(t, riding) on the compute stream, then the riding matrix moves one rank on.
     // riding_is_input == true : the kernel only reads the riding matrix.  Three buffers are
@@ -148,15 +154,16 @@ protected:
     // riding_is_input == false: the kernel accumulates into the riding matrix (fusion-1 SpMM):
     //     kernel -> shift strictly alternate, `steps` shifts, the result ends up in `home`.
     template <class Body>
-    void ring_dense(DenseMatrix &home, hnh::Comm &world, bool riding_is_input, const string &shift_key,
+    void ring_dense(DenseMatrix &home, std::shared_ptr<hnh::Comm> world_ptr, bool riding_is_input, const string &shift_key,
                     const string &compute_key, Body body);
 };
 
 // ------------------------------------------------------------------ ring driver ----------
 template <class Body>
-void Distributed_Sparse::ring_dense(DenseMatrix &home, hnh::Comm &world, bool riding_is_input,
+void Distributed_Sparse::ring_dense(DenseMatrix &home, std::shared_ptr<hnh::Comm> world_ptr, bool riding_is_input,
                                     const string &shift_key, const string &compute_key, Body body) {
     hnh::Runtime &rt = hnh::Runtime::get();
+    hnh::Comm &world = *world_ptr;
     const int steps = world.size();
     const int me = world.rank();
     const int dst = pMod(me + 1, steps), src = pMod(me - 1, steps);
@@ -167,6 +174,38 @@ void Distributed_Sparse::ring_dense(DenseMatrix &home, hnh::Comm &world, bool ri
         return;
     }
     const size_t bytes = sizeof(double) * (size_t)home.size();
+    hnh::PeerRing *pr = (riding_is_input && overlap) ? peer_ring(world_ptr, bytes) : nullptr;
+    if (pr) {
+        // Copy engines push the shard of step t into the next rank's slot (t+1)%2 while kernel t
+        // runs; flags in peer memory order the two processes (no host, no SM involved).
+        rt.chain(compute(), comm());  // `home` is up to date for the first push
+        for (int t = 0; t < steps; t++) {
+            const int k = t & 1;
+            const void *cur = t == 0 ? (const void *)home.data() : pr->slot(k);
+            if (t >= 1) pr->expect_arrival(k);
+            if (t + 1 < steps) {
+                region_begin(shift_key, comm());
+                if (t >= 1) pr->wait_arrival(k, comm());
+                pr->push((t + 1) & 1, cur, bytes, comm());
+                region_end(shift_key, comm());
+            }
+            if (t >= 1) pr->wait_arrival(k, compute());
+            region_begin(compute_key, compute());
+            if (t == 0) {
+                body(t, home);
+            } else {
+                DenseMatrix shard = DenseMatrix::view((double *)pr->slot(k), home.rows(), home.cols());
+                body(t, shard);
+            }
+            region_end(compute_key, compute());
+            if (t >= 1) {
+                rt.chain(compute(), comm());  // slot k is free once kernel t and push t are done
+                pr->release(k, comm());
+            }
+        }
+        rt.chain(comm(), compute());
+        return;
+    }
     if (riding_is_input && overlap) {
         DenseMatrix e1(home.rows(), home.cols()), e2(home.rows(), home.cols());
         DenseMatrix *bufs[3] = {&home, &e1, &e2};

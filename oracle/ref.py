@@ -63,6 +63,9 @@ def lib():
         L.ref_benchmark.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
                                     C.c_char_p, C.c_char_p, C.c_int]
         L.ref_benchmark.restype = None
+        L.ref_time_fused.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                     C.c_int, P]
+        L.ref_time_fused.restype = C.c_int64
         _LIB = L
     return _LIB
 
@@ -152,3 +155,12 @@ def benchmark(alg, p, c, R, logM, nnz_per_row, seed, fused=True, app="vanilla", 
               threads_per_rank=1):
     lib().ref_benchmark(alg.encode(), p, c, R, logM, nnz_per_row, seed, int(fused), app.encode(),
                         output_file.encode(), threads_per_rank)
+
+
+def time_fused(alg, p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per_rank):
+    """Seconds of each of (warmup + steps) fusedSpMM(A, B, S, result, Amat) calls of the REFERENCE
+    (its own loadTuples -> algorithm -> kernels), benchmark inputs.  Returns (dist_nnz, seconds[])."""
+    secs = np.zeros(warmup + steps)
+    nnz = lib().ref_time_fused(alg.encode(), p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per_rank,
+                               secs.ctypes.data)
+    return int(nnz), secs

@@ -271,4 +271,40 @@ void ref_benchmark(const char *alg, int p, int c, int R, int logM, int nnz_per_r
     hmpi_run(p, threads_per_rank, bench_main, &a);
 }
 
+
+// Times (warmup + steps) calls of the reference's fusedSpMM(A, B, S, result, Amat) on its own
+// generator path with the benchmark's inputs (A = B = 0.001, S = 1: benchmark_dist.cpp:102-106).
+// seconds_out[warmup + steps]: wall seconds of every call (max over ranks).  Returns dist_nnz.
+struct TimeArgs { int logM, nnz_per_row, R, c, calls; const char *alg; double *secs; int64_t nnz; std::mutex mu; };
+static void time_main(int rank, void *arg) {
+    TimeArgs &a = *(TimeArgs *)arg;
+    initialize_mpi_datatypes();
+    SpmatLocal S;
+    S.loadTuples(false, a.logM, a.nnz_per_row, "");
+    StandardKernel kernel;
+    Distributed_Sparse *d = make_alg(a.alg, &S, a.R, a.c, &kernel);
+    DenseMatrix A = d->like_A_matrix(0.001), B = d->like_B_matrix(0.001);
+    VectorXd Sv = d->like_S_values(1.0), res = d->like_S_values(0.0);
+    for (int t = 0; t < a.calls; t++) {
+        MPI_Barrier(MPI_COMM_WORLD);
+        const double t0 = MPI_Wtime();
+        d->fusedSpMM(A, B, Sv, res, Amat);
+        MPI_Barrier(MPI_COMM_WORLD);
+        const double dt = MPI_Wtime() - t0;
+        std::lock_guard<std::mutex> lk(a.mu);
+        a.secs[t] = std::max(a.secs[t], dt);
+    }
+    if (rank == 0) a.nnz = (int64_t)S.dist_nnz;
+    delete d;
+}
+int64_t ref_time_fused(const char *alg, int p, int c, int R, int logM, int nnz_per_row, uint64_t seed, int warmup, int steps,
+                       int threads_per_rank, double *seconds_out) {
+    hnh_shim_er_seed = seed;
+    TimeArgs a;
+    a.logM = logM; a.nnz_per_row = nnz_per_row; a.R = R; a.c = c; a.calls = warmup + steps; a.alg = alg; a.secs = seconds_out; a.nnz = 0;
+    for (int t = 0; t < a.calls; t++) seconds_out[t] = 0.0;
+    hmpi_run(p, threads_per_rank, time_main, &a);
+    return a.nnz;
+}
+
 }  // extern "C"

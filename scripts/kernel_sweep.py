@@ -10,8 +10,31 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import algorithmic_bytes, build_csr, generate_er, measured_peaks  # noqa: E402
+from bench import algorithmic_bytes, measured_peaks  # noqa: E402
 from distributed_sddmm_b200 import check, lib  # noqa: E402
+
+
+def generate_er(L, logM, npr, seed, row_lo, row_hi):
+    cap = (row_hi - row_lo) * npr
+    r = np.empty(cap, np.uint64)
+    c = np.empty(cap, np.uint64)
+    v = np.empty(cap, np.float64)
+    n = L.hnh_er_generate_host(logM, npr, seed, row_lo, row_hi, r.ctypes.data, c.ctypes.data, v.ctypes.data, cap)
+    assert n >= 0
+    return r[:n], c[:n], v[:n]
+
+
+def build_csr(L, rows, cols, r, c, v):
+    nnz = len(r)
+    rs = np.empty(rows + 1, np.int64)
+    ci = np.empty(max(nnz, 1), np.int64)
+    ri = np.empty(max(nnz, 1), np.int64)
+    vv = np.empty(max(nnz, 1), np.float64)
+    rc = L.hnh_coo_to_csr_host(rows, cols, nnz, r.ctypes.data, c.ctypes.data, v.ctypes.data, 0, rs.ctypes.data,
+                               ci.ctypes.data, ri.ctypes.data, vv.ctypes.data)
+    assert rc == 0
+    return rs, ci[:nnz], ri[:nnz], vv[:nnz]
+
 
 L = lib()
 dev = torch.device("cuda:0")
