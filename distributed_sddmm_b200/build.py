@@ -61,7 +61,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out.decode())
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", OUT, *objs, "-lnccl", "-lgomp"]
     subprocess.check_call(link)
+    # stand-alone C++ driver with the reference's command line (tools/bench_er.cpp)
+    exe = os.path.join(HERE, "bench_er")
+    subprocess.check_call([nvcc, "-O2", "-std=c++17", "-ccbin", "/usr/bin/g++", "-Wno-deprecated-gpu-targets",
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "tools", "bench_er.cpp"),
+                           "-o", exe, "-L" + HERE, "-lhnh_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
+    build_reference_driver()
     return OUT
+
+
+def build_reference_driver() -> str | None:
+    """Drop-in proof: compile the REFERENCE's own bench_erdos_renyi.cpp, unchanged (fed through stdin so
+    that its `#include "benchmark_dist.hpp"` resolves to include/hnh/compat), against this library.  Only
+    where /root/reference exists; the binary (git-ignored) travels to the GPU box."""
+    src = "/root/reference/bench_erdos_renyi.cpp"
+    if not os.path.exists(src):
+        return None
+    exe = os.path.join(HERE, "bench_er_reference_main")
+    obj = os.path.join(HERE, "build", "bench_er_reference_main.o")
+    with open(src, "rb") as f:
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-x", "c++", "-c", "-o", obj,
+                               "-I" + os.path.join(ROOT, "include", "hnh", "compat"), "-I" + os.path.join(ROOT, "include"),
+                               "-I/usr/local/cuda/include", "-"], stdin=f, cwd="/tmp")
+    subprocess.check_call(["/usr/bin/g++", "-o", exe, obj, "-L" + HERE, "-lhnh_b200", "-Wl,-rpath,$ORIGIN"])
+    return exe
 
 
 if __name__ == "__main__":
