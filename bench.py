@@ -142,6 +142,21 @@ def workload_config(args, where, **extra):
 
 
 # ------------------------------------------------------------------ CPU arm ---------------
+class _quiet_stdout:
+    """The reference prints progress with cout; keep bench.py's stdout to the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
 def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
     """GFLOP/s of the reference's fusedSpMM on the host cores (rank 0 only).  Uses oracle/_ref
     (the reference's own code) when built, else the C port of its kernels.  The sample is the
@@ -154,7 +169,8 @@ def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
     except Exception:  # noqa: BLE001
         pass
     if ref.available():
-        nnz0, s0 = ref.time_fused(args.alg, 1, 1, args.R, min(args.logM, 16), args.nnz_per_row, SEED, 1, 1, cores)
+        with _quiet_stdout():
+            nnz0, s0 = ref.time_fused(args.alg, 1, 1, args.R, min(args.logM, 16), args.nnz_per_row, SEED, 1, 1, cores)
         gf0 = 4.0 * nnz0 * args.R / s0[-1] / 1e9
         logM = args.logM
         while logM > 16:
@@ -163,7 +179,8 @@ def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
             if (warmup + steps + 6) * flop / (gf0 * 1e9) <= budget_s:
                 break
             logM -= 1
-        nnz, secs = ref.time_fused(args.alg, 1, 1, args.R, logM, args.nnz_per_row, SEED, warmup, steps, cores)
+        with _quiet_stdout():
+            nnz, secs = ref.time_fused(args.alg, 1, 1, args.R, logM, args.nnz_per_row, SEED, warmup, steps, cores)
         per = secs[warmup:]
         gf = 4.0 * nnz * args.R / per / 1e9
         desc = (f"the reference's own code (oracle/_ref: reference sources compiled unmodified; MKL/MPI/Eigen/"

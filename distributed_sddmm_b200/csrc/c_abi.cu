@@ -183,6 +183,33 @@ static int split_max_r() {
     return v;
 }
 
+// ---- TMA-staged launchers (HNH_FLAG_TMA_STAGE; r in {128, 256}, 16-byte aligned X) ------------
+template <int R, bool FUSED>
+int launch_tma(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows, const double *X,
+               const double *Y, double *Out, bool bv, bool bo, cudaStream_t st) {
+    int grid;
+    auto k = bv ? (bo ? tma_row_kernel<R, 4, FUSED, true, true> : tma_row_kernel<R, 4, FUSED, true, false>)
+                : (bo ? tma_row_kernel<R, 4, FUSED, false, true> : tma_row_kernel<R, 4, FUSED, false, false>);
+    int rc = grid_for(k, kBlock, 8, rows, &grid);
+    if (rc) return rc;
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "tma_row_kernel launch");
+}
+// Default choice between the TMA-staged and the direct-load row kernels, from the round-1 sweep
+// (profiles/r01_tma_vs_direct.md): SDDMM gains 2-8 % with TMA staging at r = 128 and 256; the fused
+// kernel gains 9 % at r = 256 (BETA0) but loses 13 % at r = 128 (the per-tile barrier makes the 8 warps
+// of a CTA wait for the longest of their rows).  HNH_TMA=0 / 1 forces one or the other everywhere.
+static bool tma_default(bool fused, int r, bool overwrite_out) {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("HNH_TMA");
+        v = e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }
+    if (v >= 0) return v == 1;
+    return fused ? (r == 256 && overwrite_out) : true;
+}
+
 // Shape table: R -> (G lanes per row, VW doubles per vector load, UN rows in flight).
 // 256-bit loads (VW=4) need 32-byte aligned operand rows; 128-bit (VW=2) need 16.
 #define HNH_DISPATCH_R(r, WIDE, CALL4, CALL2, FALLBACK)          \
@@ -246,6 +273,11 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         }                                                                                    \
     }
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
+    if (((flags & HNH_FLAG_TMA_STAGE) || (tma_default(false, r, beta0) && !(flags & HNH_FLAG_FORCE_DIRECT))) && a32 &&
+        (r == 128 || r == 256) && !(flags & HNH_FLAG_FORCE_GENERIC)) {
+        return r == 128 ? launch_tma<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st)
+                        : launch_tma<256, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st);
+    }
     if ((flags & HNH_FLAG_FORCE_GENERIC) || !a16 || !table_r) {
         if (beta0) {  // the any-r kernel accumulates: clear first
             rc = check_cuda(cudaMemsetAsync(values, 0, sizeof(double) * (size_t)nnz, st), "cudaMemsetAsync");
@@ -371,6 +403,13 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         }                                                                                    \
     }
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
+    // in place (Out == X) is not offered with TMA staging: the next tile of X is prefetched while
+    // the current one is still being written
+    if (((flags & HNH_FLAG_TMA_STAGE) || (tma_default(true, r, bo) && !(flags & HNH_FLAG_FORCE_DIRECT))) && a32 &&
+        (r == 128 || r == 256) && X != Out && !(flags & HNH_FLAG_FORCE_GENERIC)) {
+        return r == 128 ? launch_tma<128, true>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)
+                        : launch_tma<256, true>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st);
+    }
     if ((flags & HNH_FLAG_FORCE_GENERIC) || !a16 || !table_r) {
         if (X == Out)
             return set_error(HNH_E_INVALID, "hnh_fused_f64: in-place (Out == X) needs a table r "

@@ -326,6 +326,146 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
     }
 }
 
+// ------------------------------------------------------------------ TMA-staged variants ---
+// The row-side factor tile X[row0 .. row0+TR) of the TR = 8 rows a CTA works on is one contiguous
+// TR*R*8-byte span: a single elected thread fetches it with ONE bulk asynchronous copy
+// (cp.async.bulk.shared::cluster.global, SASS UBLKCP) that signals an mbarrier, and -- because each
+// warp moves its row into registers as soon as the tile has landed -- the copy of the NEXT tile is
+// issued right away and flies while the current tile's rows are being gathered.  The X stream thus
+// costs no LSU instruction and no exposed latency.  The gathered Y rows stay direct 256-bit loads
+// into registers (random 8R-byte rows consumed once: staging them would add a shared-memory hop
+// and remove no HBM traffic).  Selected with HNH_FLAG_TMA_STAGE; compared with the direct-load
+// kernels in profiles/.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "HNH_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra HNH_DONE;\n"
+        "bra HNH_WAIT;\n"
+        "HNH_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// FUSED == false: SDDMM (values (+)= X.Y).  FUSED == true: SDDMM -> SpMM with one gather.
+template <int R, int UN, bool FUSED, bool BV, bool BO>
+__global__ void __launch_bounds__(256)
+tma_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx, double *__restrict__ values,
+               int64_t rows, const double *X, const double *__restrict__ Y, double *Out) {
+    constexpr int G = 32, VW = 4, TR = 8;
+    constexpr int NV = R / (G * VW);
+    static_assert(NV * G * VW == R, "R must be a multiple of 128");
+    __shared__ alignas(128) double xs[TR][R];
+    __shared__ alignas(8) uint64_t bar;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned gmask = 0xffffffffu;
+    const int64_t ntiles = (rows + TR - 1) / TR;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    int64_t tile = blockIdx.x;
+    auto issue = [&](int64_t t) {
+        const int64_t r0 = t * TR;
+        const int64_t nr = rows - r0 < TR ? rows - r0 : TR;
+        bulk_load(&xs[0][0], X + r0 * R, (unsigned)(nr * R * sizeof(double)), &bar);
+    };
+    if (threadIdx.x == 0 && tile < ntiles) issue(tile);
+    unsigned parity = 0;
+    for (; tile < ntiles; tile += gridDim.x) {
+        const int64_t row = tile * TR + w;
+        mbar_wait(&bar, parity);
+        parity ^= 1;
+        double x[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int q = 0; q < VW; q++) x[v][q] = xs[w][(v * G + lane) * VW + q];
+        __syncthreads();  // every warp holds its row in registers: the tile buffer is free again
+        if (threadIdx.x == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x);  // prefetch
+        if (row >= rows) continue;
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        double acc[NV][VW];
+        if (FUSED) {
+            if (!BO && s == e) continue;
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                if (BO) {
+#pragma unroll
+                    for (int q = 0; q < VW; q++) acc[v][q] = 0.0;
+                } else {
+                    ld_rw<VW>(acc[v], Out + row * R + (v * G + lane) * VW);
+                }
+            }
+        }
+        for (int64_t j = s; j < e; j += G) {
+            const int cnt = (e - j < G) ? (int)(e - j) : G;
+            int64_t mycol = 0;
+            double myval = 0.0;
+            if (lane < cnt) {
+                mycol = ld_stream_i64(col_idx + j + lane);
+                if (!BV) myval = values[j + lane];
+            }
+            for (int k0 = 0; k0 < cnt; k0 += UN) {
+                double y[UN][NV][VW];
+                double vold[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int k = k0 + u;
+                    const int src = k < G ? k : G - 1;
+                    const int64_t c = __shfl_sync(gmask, mycol, src, G);
+                    vold[u] = __shfl_sync(gmask, myval, src, G);
+                    if (k < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++) ld_gather<VW>(y[u][v], Y + c * R + (v * G + lane) * VW);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int q = 0; q < VW; q++) y[u][v][q] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int q = 0; q < VW; q++) d = fma(x[v][q], y[u][v][q], d);
+                    d = group_allreduce<G>(d, gmask);
+                    const double vnew = vold[u] + d;
+                    if (lane == k0 + u) myval = vnew;
+                    if (FUSED && k0 + u < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int q = 0; q < VW; q++) acc[v][q] = fma(vnew, y[u][v][q], acc[v][q]);
+                    }
+                }
+            }
+            if (lane < cnt) values[j + lane] = myval;
+        }
+        if (FUSED) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) st_rw<VW>(Out + row * R + (v * G + lane) * VW, acc[v]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ small-r kernels ------
 // For narrow factors (r <= 32) a row is too short to feed a whole warp, so the G = GK*GN lanes
 // that own a CSR row are laid out in two dimensions: GK lanes split the r columns (VW doubles

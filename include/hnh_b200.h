@@ -47,6 +47,12 @@ extern "C" {
 /* fused only: overwrite just the values (each block is visited once per FusedMM) or just Out */
 #define HNH_FLAG_BETA0_VALUES 16
 #define HNH_FLAG_BETA0_OUT 32
+/* sddmm / fused, r in {128, 256}: stage the row-side factor tile with bulk asynchronous copies
+ * (cp.async.bulk + mbarrier, SASS UBLKCP) instead of direct loads.  Without this flag the library picks
+ * per kernel from measurements (TMA for SDDMM and for the r = 256 overwrite-fused kernel; direct loads
+ * otherwise); HNH_FLAG_FORCE_DIRECT or env HNH_TMA=0 force the direct-load kernels, HNH_TMA=1 the
+ * TMA-staged ones. */
+#define HNH_FLAG_TMA_STAGE 64
 
 /* ABI / build identification. */
 int hnh_abi_version(void);

@@ -256,3 +256,31 @@ def test_beta0_overwrite_variants(hnh, R):
         dA = gu.dev(A)
         assert hnh.hnh_fused_f64(dA.data_ptr(), dA.data_ptr(), dA.data_ptr(), N, csr.nnz, dA.data_ptr(),
                                  dA.data_ptr(), dA.data_ptr(), R, BETA0, gu.stream()) == -1
+
+
+@pytest.mark.parametrize("R", [128, 256])
+def test_tma_staged_variants_match_oracle(hnh, R):
+    """HNH_FLAG_TMA_STAGE: the X tile arrives by cp.async.bulk + mbarrier; results must be identical in
+    value to the direct-load kernels (same arithmetic order).  Row count not a multiple of the tile."""
+    TMA, BETA0 = 64, 4
+    rng = np.random.default_rng(21)
+    M, N = 1003, 777
+    r = rng.integers(0, M, 9000).astype(np.uint64)
+    c = rng.integers(0, N, 9000).astype(np.uint64)
+    order = np.lexsort((r, c))
+    r, c = r[order], c[order]
+    csr = orc.coo_to_csr(M, N, r, c, np.ones(len(r)))
+    A, B = rng.uniform(-1, 1, (M, R)), rng.uniform(-1, 1, (N, R))
+    v0, O0 = rng.uniform(-1, 1, csr.nnz), rng.uniform(-1, 1, (M, R))
+    ref = orc.sddmm_coo(csr.row_idx, csr.col_idx, v0.copy(), A, B)
+    direct = gu.run_sddmm(csr, A, B, v0, flags=2)  # HNH_FLAG_FORCE_DIRECT
+    tma = gu.run_sddmm(csr, A, B, v0, flags=TMA)
+    assert rel_err(tma, ref) < RTOL and np.array_equal(tma, direct)
+    assert rel_err(gu.run_sddmm(csr, A, B, v0, flags=TMA | BETA0), orc.sddmm_coo(csr.row_idx, csr.col_idx, np.zeros(csr.nnz), A, B)) < RTOL
+    vref, oref = orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, v0.copy(), A, B, O0.copy())
+    v, o = gu.run_fused(csr, v0, A, B, O0, flags=TMA)
+    vd, od = gu.run_fused(csr, v0, A, B, O0, flags=2)
+    assert rel_err(v, vref) < RTOL and rel_err(o, oref) < RTOL and np.array_equal(v, vd) and np.array_equal(o, od)
+    vref0, oref0 = orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), A, B, np.zeros((M, R)))
+    v, o = gu.run_fused(csr, v0, A, B, O0, flags=TMA | BETA0)
+    assert rel_err(v, vref0) < RTOL and rel_err(o, oref0) < RTOL
