@@ -38,9 +38,12 @@ def run_cases(nproc, cases, transport, timeout=600):
         return out
 
 
-def case(alg, c, R, logM, npr, seed=0xC0FFEE + 1, script=ALL_OPS, name=None, load="tuples"):
-    return dict(name=name or f"{alg}_c{c}_R{R}_m{logM}", alg=alg, c=c, R=R, logM=logM, npr=npr, seed=seed,
-                script=list(script), load=load)
+def case(alg, c, R, logM, npr, seed=0xC0FFEE + 1, script=ALL_OPS, name=None, load="tuples", n=None):
+    d = dict(name=name or f"{alg}_c{c}_R{R}_m{logM}" + (f"_n{n}" if n else ""), alg=alg, c=c, R=R, logM=logM, npr=npr,
+             seed=seed, script=list(script), load=load)
+    if n:
+        d["n"] = n
+    return d
 
 
 def reference_for(case_, p):
@@ -48,8 +51,10 @@ def reference_for(case_, p):
     from oracle import hnh_oracle as orc
     from oracle import ref
     from tests.mp_worker import global_inputs, sval
-    N = 1 << case_["logM"]
-    rows, cols, _ = orc.er_tuples(case_["logM"], case_["npr"], case_["seed"])
+    N = case_.get("n") or (1 << case_["logM"])
+    rows, cols, _ = orc.er_tuples(case_["logM"], case_["npr"], case_["seed"], 0, N)
+    keep = cols < N
+    rows, cols = rows[keep], cols[keep]
     A, B = global_inputs(N, case_["R"], case_["seed"])
     golden = os.path.join(ROOT, "tests", "golden", f"{case_['name']}_p{p}.npz")
     if ref.available():

@@ -53,7 +53,7 @@ def main():
     rank, world = D.world_init(transport)
     for case in cases:
         name, alg_name, c, R, logM, npr, seed, script = (case[k] for k in ("name", "alg", "c", "R", "logM", "npr", "seed", "script"))
-        N = 1 << logM
+        N = case.get("n") or (1 << logM)  # "n": a size that does not divide evenly among the ranks
         if case.get("load", "tuples") == "er":
             # SpmatLocal::loadTuples(false, logM, npr, ""): every rank generates its row slice, values 1.0
             S = D.SpmatLocal.load_er(logM, npr, seed)
@@ -63,6 +63,8 @@ def main():
             per = N // world
             lo, hi = per * rank, (N if rank == world - 1 else per * (rank + 1))
             tr, tc, _ = orc.er_tuples(logM, npr, seed, lo, hi)
+            keep = tc < N
+            tr, tc = tr[keep], tc[keep]
             S = D.SpmatLocal.from_tuples(N, N, tr, tc, sval(tr, tc))
         alg = D.Algorithm(alg_name, S, R, c)
         d = alg.dims
@@ -79,7 +81,7 @@ def main():
                         out[f"{key}_b{b}_{f}"] = blk[f]
         if have_gpu and script:
             A, B = alg.like_A_matrix(), alg.like_B_matrix()
-            GA, GB = global_inputs(N, R, seed)
+            GA, GB = global_inputs(N, R, seed)  # same N as the reference side
             shapeA, shapeB = (d.localArows, d.localAcols), (d.localBrows, d.localBcols)
             subsA, subsB = alg.submatrices("A"), alg.submatrices("B")
 

@@ -1,0 +1,55 @@
+"""Golden fixtures stay in sync with the reference build; bench.py's reference arm honours the JSON contract."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import mp_util as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_golden_files_match_fresh_reference_run():
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built on this box")
+    from tests.test_multirank_gpu import CASES
+    checked = 0
+    for p, c in ((2, CASES[2][0]), (4, CASES[4][5]), (2, CASES[2][7])):
+        path = os.path.join(ROOT, "tests", "golden", f"{c['name']}_p{p}.npz")
+        assert os.path.exists(path), f"missing golden file {path}: run scripts/make_golden.py"
+        fresh, src = U.reference_for(c, p)
+        assert src == "oracle/_ref"
+        gold = U.load_golden(path, p)
+        for f, g in zip(fresh, gold):
+            assert np.array_equal(f["S_rows"], g["S_rows"]) and np.array_equal(f["ST_cols"], g["ST_cols"])
+            for t in range(len(f["ops"])):
+                for k in ("A", "B", "values"):
+                    assert np.array_equal(f["ops"][t][k], g["ops"][t][k]), (c["name"], t, k)
+        checked += 1
+    assert checked == 3
+
+
+def test_bench_reference_arm_contract():
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--logM", "12", "--nnz-per-row", "8", "--R", "16"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, "exactly one line on stdout"
+    rec = json.loads(lines[0])
+    assert rec["impl"] == "reference" and rec["unit"] == "GFLOP/s" and rec["higher_is_better"] is True
+    assert rec["value"] > 0 and rec["dtype"] == "f64" and "workload" in rec["config"]
+    assert rec["cpu_baseline"]["kind"] in ("reference", "port") and rec["cpu_baseline"]["cores"] >= 1
+    assert rec["e2e"]["h2d_bytes_per_step"] == 0 and rec["e2e"]["value"] == rec["value"]
+
+
+def test_bench_native_refuses_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("box has a GPU")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT)
+    assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)

@@ -14,12 +14,17 @@ CASES_2 = [
     U.case("15d_fusion2", 2, 8, 7, 5),
     U.case("15d_sparse", 2, 8, 7, 5),
     U.case("25d_sparse_replicate", 2, 8, 7, 5),
+    # sizes that do not divide evenly: trailing blocks are padded (ceil-div sizing, common.cpp:20-27)
+    U.case("15d_fusion2", 1, 8, 7, 5, n=101),
+    U.case("15d_sparse", 1, 8, 7, 5, n=101),
 ]
 CASES_4 = [
     U.case("15d_fusion1", 2, 8, 7, 5),
     U.case("15d_sparse", 1, 8, 7, 5),
     U.case("25d_dense_replicate", 1, 8, 7, 5),
     U.case("25d_sparse_replicate", 1, 8, 7, 5),
+    U.case("15d_fusion1", 2, 8, 7, 5, n=99),
+    U.case("25d_dense_replicate", 1, 8, 7, 5, n=99),
 ]
 
 

@@ -17,12 +17,14 @@ CASES = {
     2: [U.case("15d_fusion1", 1, 8, 7, 5), U.case("15d_fusion1", 2, 8, 7, 5), U.case("15d_fusion2", 1, 8, 7, 5),
         U.case("15d_fusion2", 2, 8, 7, 5), U.case("15d_sparse", 1, 8, 7, 5), U.case("15d_sparse", 2, 8, 7, 5),
         U.case("25d_sparse_replicate", 2, 8, 7, 5),
+        U.case("15d_fusion2", 1, 8, 7, 5, n=101), U.case("15d_sparse", 1, 8, 7, 5, n=101),  # padded trailing blocks
         # wide factors (the r = 128 kernels); too large for a golden file: needs oracle/_ref
         U.case("15d_fusion2", 1, 128, 9, 6, name="nogolden_fusion2_r128"),
         U.case("15d_fusion1", 1, 128, 9, 6, name="nogolden_fusion1_r128")],
     4: [U.case("15d_fusion1", 2, 8, 7, 5), U.case("15d_fusion2", 1, 16, 7, 5), U.case("15d_fusion2", 4, 8, 7, 5),
         U.case("15d_sparse", 1, 8, 7, 5), U.case("15d_sparse", 2, 32, 7, 5), U.case("25d_dense_replicate", 1, 8, 7, 5),
-        U.case("25d_sparse_replicate", 1, 8, 7, 5)],
+        U.case("25d_sparse_replicate", 1, 8, 7, 5),
+        U.case("15d_fusion1", 2, 8, 7, 5, n=99), U.case("25d_dense_replicate", 1, 8, 7, 5, n=99)],
     8: [U.case("15d_fusion1", 2, 8, 8, 5), U.case("15d_fusion2", 1, 8, 8, 5), U.case("15d_sparse", 1, 32, 8, 5),
         U.case("25d_dense_replicate", 2, 8, 8, 5), U.case("25d_sparse_replicate", 2, 8, 8, 5),
         U.case("15d_fusion2", 2, 128, 10, 6, name="nogolden_fusion2_r128_p8")],
