@@ -62,10 +62,19 @@ def world_init(transport: str | None = None):
     return L.hnhd_world_rank(), L.hnhd_world_size()
 
 
-def world_finalize():
+def world_finalize(destroy_process_group: bool = True):
+    """MPI_Finalize of this library; also tears the torch.distributed group down cleanly."""
     global _transport_keepalive
     check(lib().hnhd_finalize(), "hnhd_finalize")
     _transport_keepalive = None
+    if destroy_process_group:
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier()
+                dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class SpmatLocal:

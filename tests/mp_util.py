@@ -26,6 +26,9 @@ def run_cases(nproc, cases, transport, timeout=600):
                os.path.join(ROOT, "tests", "mp_worker.py"), json.dumps(cases), td, transport]
         env = dict(os.environ, OMP_NUM_THREADS="2")
         p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, text=True)
+        if p.returncode != 0 and "Address already in use" in p.stdout:  # lost the race for the rendezvous port
+            cmd[cmd.index("--master-port") + 1] = str(free_port())
+            p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, text=True)
         if p.returncode != 0:
             raise RuntimeError("worker failed:\n" + p.stdout[-6000:])
         out = {}

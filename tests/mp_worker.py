@@ -139,7 +139,7 @@ def main():
         out["info"] = json.dumps(alg.info())
         np.savez(os.path.join(outdir, f"{name}_rank{rank}.npz"), **out)
         del alg, S
-    D.world_finalize()
+    D.world_finalize()  # also destroys the torch.distributed group (clean gloo teardown)
 
 
 if __name__ == "__main__":
