@@ -211,3 +211,44 @@ hnh::PeerRing *Distributed_Sparse::peer_ring(std::shared_ptr<hnh::Comm> world, s
     }
     return peer_rings_[key].get();
 }
+
+hnh::PeerRing *Distributed_Sparse::sparse_ring(std::shared_ptr<hnh::Comm> world, CSRLocal *blk) {
+    if (peer_ring_broken_ || !hnh::PeerRing::all_shifts() || world->size() < 2 || blk == nullptr) return nullptr;
+    auto key = std::make_pair(world.get(), blk);
+    auto it = sparse_rings_.find(key);
+    if (it != sparse_rings_.end()) return it->second.get();
+    try {
+        sparse_rings_[key].reset(new hnh::PeerRing(world, blk->ring_buffers(), blk->active));
+    } catch (const hnh::Error &e) {
+        if (verbose) cout << "sparse PeerRing unavailable, using NCCL send/recv: " << e.what() << endl;
+        sparse_rings_.erase(key);
+        peer_ring_broken_ = true;
+        return nullptr;
+    }
+    return sparse_rings_[key].get();
+}
+
+// logical buffers of CSRLocal::ring_buffers(): 0 = values, 1 = col_idx, 2 = rowStart
+void Distributed_Sparse::sparse_push_early(hnh::PeerRing &pr, CSRLocal &blk, bool values_written) {
+    const int k = 1 - blk.active;  // the downstream rank's passive handle (all ranks flip together)
+    CSRHandle *h = blk.getActive();
+    pr.begin_push(k, comm());
+    const size_t nz = (size_t)blk.num_coords;
+    if (nz) hnh::cuda_check(cudaMemcpyAsync(pr.dst_ptr(1, k), h->col_idx.data(), sizeof(int64_t) * nz, cudaMemcpyDeviceToDevice, comm()), "push col_idx");
+    hnh::cuda_check(cudaMemcpyAsync(pr.dst_ptr(2, k), h->rowStart.data(), sizeof(int64_t) * (size_t)(blk.rows + 1), cudaMemcpyDeviceToDevice, comm()), "push rowStart");
+    if (!values_written && nz)
+        hnh::cuda_check(cudaMemcpyAsync(pr.dst_ptr(0, k), h->values.data(), sizeof(double) * nz, cudaMemcpyDeviceToDevice, comm()), "push values");
+}
+
+void Distributed_Sparse::sparse_push_late(hnh::PeerRing &pr, CSRLocal &blk, bool values_written, bool early_done, int64_t incoming) {
+    const int a = blk.active, k = 1 - a;
+    if (!early_done) sparse_push_early(pr, blk, false);  // everything in one go, after the kernel
+    else if (values_written && blk.num_coords)
+        hnh::cuda_check(cudaMemcpyAsync(pr.dst_ptr(0, k), blk.getActive()->values.data(), sizeof(double) * (size_t)blk.num_coords,
+                                        cudaMemcpyDeviceToDevice, comm()), "push values");
+    pr.end_push(k, comm());
+    pr.release(a, comm());  // my handle `a` has been read by the kernel and by the push: upstream may refill it
+    blk.shift_commit(incoming);
+    pr.expect_arrival(k);
+    pr.wait_arrival(k, comm());
+}

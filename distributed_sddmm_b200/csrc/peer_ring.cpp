@@ -38,11 +38,12 @@ void cu_check(CUresult r, const char *what) {
     if (r != CUDA_SUCCESS) throw Error(HNH_E_CUDA, std::string(what) + " failed (CUresult " + std::to_string((int)r) + ")");
 }
 
+constexpr int kMaxBuffers = 4;
 struct Handles {
-    cudaIpcMemHandle_t slot[2];
+    cudaIpcMemHandle_t buf[kMaxBuffers][2];
     cudaIpcMemHandle_t flags;
+    int nbuf;
     int device;
-    int pid_marker;
 };
 
 }  // namespace
@@ -52,39 +53,71 @@ bool PeerRing::enabled() {
     return !(e && std::strcmp(e, "nccl") == 0);
 }
 
+bool PeerRing::all_shifts() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HNH_RING_ALL");
+        v = e ? (atoi(e) != 0 ? 1 : 0) : 1;
+    }
+    return v == 1 && enabled();
+}
+
 PeerRing::PeerRing(std::shared_ptr<Comm> ring, size_t slot_bytes) : ring_(std::move(ring)), bytes_(slot_bytes) {
     if (ring_->size() < 2) throw Error(HNH_E_INVALID, "PeerRing needs at least two ranks");
+    // plain cudaMalloc: IPC handles need whole allocations that are never recycled for something else
+    for (int k = 0; k < 2; k++) cuda_check(cudaMalloc(&slot_[k], bytes_ ? bytes_ : 256), "cudaMalloc(ring slot)");
+    owns_slots_ = true;
+    connect({{slot_[0], slot_[1]}}, -1);
+}
+
+PeerRing::PeerRing(std::shared_ptr<Comm> ring, const std::vector<std::array<void *, 2>> &external, int resident_slot)
+    : ring_(std::move(ring)), bytes_(0) {
+    if (ring_->size() < 2) throw Error(HNH_E_INVALID, "PeerRing needs at least two ranks");
+    if (external.empty() || (int)external.size() > kMaxBuffers) throw Error(HNH_E_INVALID, "PeerRing: 1..4 logical buffers");
+    connect(external, resident_slot);
+}
+
+void PeerRing::connect(const std::vector<std::array<void *, 2>> &local, int resident_slot) {
     load_driver();
     int dev = 0;
     cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
-    int can = 0;
-    cuda_check(cudaDeviceGetAttribute(&can, cudaDevAttrIpcEventSupport, dev), "cudaDeviceGetAttribute");  // proxy for IPC support
-    // plain cudaMalloc: IPC handles need whole allocations that are never recycled for something else
-    for (int k = 0; k < 2; k++) cuda_check(cudaMalloc(&slot_[k], bytes_ ? bytes_ : 256), "cudaMalloc(ring slot)");
     cuda_check(cudaMalloc((void **)&flags_, 256), "cudaMalloc(ring flags)");
+    Flags init;
+    std::memset(&init, 0, sizeof init);
+    if (resident_slot == 0 || resident_slot == 1) {
+        init.arrived[resident_slot] = 1;
+        pushed_[resident_slot] = expected_[resident_slot] = 1;
+    }
     cuda_check(cudaMemset(flags_, 0, 256), "cudaMemset");
+    cuda_check(cudaMemcpy(flags_, &init, sizeof init, cudaMemcpyHostToDevice), "cudaMemcpy(flags)");
     cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
 
     Handles mine;
     std::memset(&mine, 0, sizeof mine);
-    for (int k = 0; k < 2; k++) cuda_check(cudaIpcGetMemHandle(&mine.slot[k], slot_[k]), "cudaIpcGetMemHandle");
-    cuda_check(cudaIpcGetMemHandle(&mine.flags, flags_), "cudaIpcGetMemHandle");
+    mine.nbuf = (int)local.size();
     mine.device = dev;
+    for (size_t i = 0; i < local.size(); i++)
+        for (int k = 0; k < 2; k++) cuda_check(cudaIpcGetMemHandle(&mine.buf[i][k], local[i][(size_t)k]), "cudaIpcGetMemHandle");
+    cuda_check(cudaIpcGetMemHandle(&mine.flags, flags_), "cudaIpcGetMemHandle");
     const int n = ring_->size(), me = ring_->rank();
     std::vector<Handles> all((size_t)n);
     ring_->host_allgather(&mine, all.data(), sizeof(Handles));
     const int dst = (me + 1) % n, src = (me + n - 1) % n;
-    auto open = [&](const cudaIpcMemHandle_t &h, void **out, int idx) {
-        cuda_check(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
-        opened_[idx] = true;
+    if (all[(size_t)dst].nbuf != mine.nbuf) throw Error(HNH_E_COMM, "PeerRing: ranks registered different buffer counts");
+    auto open = [&](const cudaIpcMemHandle_t &h) {
+        void *p = nullptr;
+        cuda_check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+        return p;
     };
-    open(all[(size_t)dst].slot[0], &dst_slot_[0], 0);
-    open(all[(size_t)dst].slot[1], &dst_slot_[1], 1);
-    open(all[(size_t)dst].flags, (void **)&dst_flags_, 2);
+    dst_.resize(local.size());
+    for (size_t i = 0; i < local.size(); i++)
+        for (int k = 0; k < 2; k++) dst_[i][(size_t)k] = open(all[(size_t)dst].buf[i][k]);
+    dst_flags_ = (Flags *)open(all[(size_t)dst].flags);
     if (src == dst) {
         src_flags_ = dst_flags_;
     } else {
-        open(all[(size_t)src].flags, (void **)&src_flags_, 3);
+        src_flags_ = (Flags *)open(all[(size_t)src].flags);
+        src_flags_opened_ = true;
     }
     ring_->barrier();
 }
@@ -96,23 +129,34 @@ PeerRing::~PeerRing() {
         ring_->barrier();
     } catch (...) {
     }
-    if (opened_[0]) cudaIpcCloseMemHandle(dst_slot_[0]);
-    if (opened_[1]) cudaIpcCloseMemHandle(dst_slot_[1]);
-    if (opened_[2]) cudaIpcCloseMemHandle(dst_flags_);
-    if (opened_[3]) cudaIpcCloseMemHandle(src_flags_);
-    cudaFree(slot_[0]);
-    cudaFree(slot_[1]);
+    for (auto &b : dst_)
+        for (int k = 0; k < 2; k++)
+            if (b[(size_t)k]) cudaIpcCloseMemHandle(b[(size_t)k]);
+    if (dst_flags_) cudaIpcCloseMemHandle(dst_flags_);
+    if (src_flags_opened_ && src_flags_) cudaIpcCloseMemHandle(src_flags_);
+    if (owns_slots_) {
+        cudaFree(slot_[0]);
+        cudaFree(slot_[1]);
+    }
     cudaFree(flags_);
 }
 
-void PeerRing::push(int k, const void *src, size_t bytes, cudaStream_t s) {
-    if (bytes > bytes_) throw Error(HNH_E_INVALID, "PeerRing::push: shard larger than the slot");
+void PeerRing::begin_push(int k, cudaStream_t s) {
     // everything pushed into downstream slot k so far must have been consumed there
     cu_check(g_wait32((CUstream)s, (CUdeviceptr)&flags_->freed[k], pushed_[k], CU_STREAM_WAIT_VALUE_GEQ), "cuStreamWaitValue32");
-    cuda_check(cudaMemcpyAsync(dst_slot_[k], src, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync(peer push)");
+}
+
+void PeerRing::end_push(int k, cudaStream_t s) {
     pushed_[k]++;
     cu_check(g_write32((CUstream)s, (CUdeviceptr)&dst_flags_->arrived[k], pushed_[k], CU_STREAM_WRITE_VALUE_DEFAULT),
              "cuStreamWriteValue32");
+}
+
+void PeerRing::push(int k, const void *src, size_t bytes, cudaStream_t s) {
+    if (owns_slots_ && bytes > bytes_) throw Error(HNH_E_INVALID, "PeerRing::push: shard larger than the slot");
+    begin_push(k, s);
+    cuda_check(cudaMemcpyAsync(dst_[0][(size_t)k], src, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync(peer push)");
+    end_push(k, s);
 }
 
 void PeerRing::expect_arrival(int k) { expected_[k]++; }

@@ -135,6 +135,15 @@ void CSRLocal::shift_values(int src, int dst, hnh::Comm &comm, int64_t nnz_in, c
                   sizeof(double) * (size_t)nnz_in, src, s);
 }
 
+std::vector<std::array<void *, 2>> CSRLocal::ring_buffers() {
+    ensure_device();
+    for (int t = 0; t < 2; t++)
+        if (!buffer[t].allocated) allocate(buffer[t]);
+    return {{buffer[0].values.data(), buffer[1].values.data()},
+            {buffer[0].col_idx.data(), buffer[1].col_idx.data()},
+            {buffer[0].rowStart.data(), buffer[1].rowStart.data()}};
+}
+
 void CSRLocal::shift_commit(int64_t nnz_received) {
     buffer[1 - active].row_idx_valid = false;
     num_coords = nnz_received;

@@ -131,15 +131,19 @@ public:
         const KernelMode local_mode = (mode == k_spmmB) ? k_spmmA : mode;
         const int me = grid->i;
         const int src = pMod(me - 1, steps), dst = pMod(me + 1, steps);
+        // copy-engine ring into the next rank's passive CSRHandle when available, NCCL send/recv otherwise
+        hnh::PeerRing *pr = steps > 1 ? sparse_ring(grid->col_world, blk) : nullptr;
         for (int t = 0; t < steps; t++) {
             const int block_id = pMod(me - t, steps);
             const int64_t incoming = nnz_in_axis[pMod(me - t - 1, steps)];
             const bool shift = steps > 1;
-            if (shift && overlap) {
+            const bool early = shift && overlap;
+            if (early) {
                 // structure (and, for SpMM, the read-only values too) leaves while the kernel runs
                 rt.chain(compute(), comm());  // the passive buffer is free: kernel t-1 has been issued before
                 region_begin("Cyclic Shift Time", comm());
-                if (sddmm) blk->shift_structure(src, dst, ring, incoming, comm());
+                if (pr) sparse_push_early(*pr, *blk, sddmm);
+                else if (sddmm) blk->shift_structure(src, dst, ring, incoming, comm());
                 else blk->shiftCSR_no_flip(src, dst, ring, incoming, comm());
                 region_end("Cyclic Shift Time", comm());
             }
@@ -157,10 +161,14 @@ public:
             if (shift) {
                 rt.chain(compute(), comm());
                 region_begin("Cyclic Shift Time", comm());
-                if (!overlap) blk->shiftCSR_no_flip(src, dst, ring, incoming, comm());
-                else if (sddmm) blk->shift_values(src, dst, ring, incoming, comm());
+                if (pr) {
+                    sparse_push_late(*pr, *blk, sddmm, early, incoming);
+                } else {
+                    if (!early) blk->shiftCSR_no_flip(src, dst, ring, incoming, comm());
+                    else if (sddmm) blk->shift_values(src, dst, ring, incoming, comm());
+                    blk->shift_commit(incoming);
+                }
                 region_end("Cyclic Shift Time", comm());
-                blk->shift_commit(incoming);
                 choice->blockStarts[1] = (uint64_t)blk->num_coords;
                 rt.chain(comm(), compute());
             }

@@ -139,13 +139,65 @@ public:
         DenseMatrix &fixed = c > 1 ? accumulation_buffer : *stationary;
 
         CSRLocal *blk = choice->csr_blocks[0];
-        BufferPair ride(riding);
         const size_t dense_bytes = sizeof(double) * (size_t)riding->size();
         const KernelMode local_mode = (mode == k_spmmA) ? k_spmmB : mode;
-        hnh::Comm &dense_ring = *grid->col_world, &sparse_ring = *grid->row_world;
+        hnh::Comm &dense_ring = *grid->col_world, &sparse_ring_comm = *grid->row_world;
         const int d_dst = pMod(grid->rankInCol + 1, s), d_src = pMod(grid->rankInCol - 1, s);
         const int s_dst = pMod(grid->rankInRow + 1, s), s_src = pMod(grid->rankInRow - 1, s);
+        auto run_kernel = [&](int t, DenseMatrix &shard) {
+            region_begin("Computation Time", compute());
+            if (sk) sk->values_are_zero = sddmm && t == 0;
+            kernel->triple_function(local_mode, *choice, fixed, shard, 0, localAcols * grid->j);
+            if (sk) sk->values_are_zero = false;
+            region_end("Computation Time", compute());
+        };
 
+        // copy-engine rings (dense shard over col_world, CSR block over row_world) when available
+        hnh::PeerRing *prd = (s > 1 && overlap && hnh::PeerRing::all_shifts()) ? peer_ring(grid->col_world, dense_bytes) : nullptr;
+        hnh::PeerRing *prs = (prd != nullptr) ? sparse_ring(grid->row_world, blk) : nullptr;
+        if (prd && prs) {
+            for (int t = 0; t < s; t++) {
+                const int64_t incoming = nnz_in_axis[pMod(sparse_shift - t - 1, s)];
+                const int kd = (t + 1) & 1;
+                const void *cur_ptr = t == 0 ? (const void *)riding->data() : prd->slot(t & 1);
+                rt.chain(compute(), comm());
+                if (sddmm) {  // the dense shard is an input: it may leave while the kernel reads it
+                    region_begin("Dense Cyclic Shift Time", comm());
+                    prd->push(kd, cur_ptr, dense_bytes, comm());
+                    region_end("Dense Cyclic Shift Time", comm());
+                }
+                region_begin("Sparse Cyclic Shift Time", comm());
+                sparse_push_early(*prs, *blk, sddmm);
+                region_end("Sparse Cyclic Shift Time", comm());
+                if (t == 0) {
+                    run_kernel(t, *riding);
+                } else {
+                    DenseMatrix shard = DenseMatrix::view((double *)prd->slot(t & 1), riding->rows(), riding->cols());
+                    run_kernel(t, shard);
+                }
+                rt.chain(compute(), comm());
+                if (!sddmm) {  // the SpMM output rides: it leaves after the kernel
+                    region_begin("Dense Cyclic Shift Time", comm());
+                    prd->push(kd, cur_ptr, dense_bytes, comm());
+                    region_end("Dense Cyclic Shift Time", comm());
+                }
+                if (t >= 1) prd->release(t & 1, comm());
+                region_begin("Sparse Cyclic Shift Time", comm());
+                sparse_push_late(*prs, *blk, sddmm, true, incoming);
+                region_end("Sparse Cyclic Shift Time", comm());
+                choice->blockStarts[1] = (uint64_t)blk->num_coords;
+                prd->expect_arrival(kd);
+                prd->wait_arrival(kd, comm());
+                rt.chain(comm(), compute());
+            }
+            // after s hops the dense shard is home again, in slot s & 1
+            if (!sddmm)
+                hnh::cuda_check(cudaMemcpyAsync(riding->data(), prd->slot(s & 1), dense_bytes, cudaMemcpyDeviceToDevice, comm()),
+                                "ring copy-back");
+            prd->release(s & 1, comm());
+            rt.chain(comm(), compute());
+        } else {
+        BufferPair ride(riding);
         for (int t = 0; t < s; t++) {
             const int64_t incoming = nnz_in_axis[pMod(sparse_shift - t - 1, s)];
             const bool shift = s > 1;
@@ -159,15 +211,11 @@ public:
                     region_end("Dense Cyclic Shift Time", comm());
                 }
                 region_begin("Sparse Cyclic Shift Time", comm());
-                if (sddmm) blk->shift_structure(s_src, s_dst, sparse_ring, incoming, comm());
-                else blk->shiftCSR_no_flip(s_src, s_dst, sparse_ring, incoming, comm());
+                if (sddmm) blk->shift_structure(s_src, s_dst, sparse_ring_comm, incoming, comm());
+                else blk->shiftCSR_no_flip(s_src, s_dst, sparse_ring_comm, incoming, comm());
                 region_end("Sparse Cyclic Shift Time", comm());
             }
-            region_begin("Computation Time", compute());
-            if (sk) sk->values_are_zero = sddmm && t == 0;
-            kernel->triple_function(local_mode, *choice, fixed, *ride.getActive(), 0, localAcols * grid->j);
-            if (sk) sk->values_are_zero = false;
-            region_end("Computation Time", compute());
+            run_kernel(t, *ride.getActive());
             if (shift) {
                 rt.chain(compute(), comm());
                 if (!early || !sddmm) {  // the SpMM output rides: it leaves after the kernel
@@ -177,8 +225,8 @@ public:
                     region_end("Dense Cyclic Shift Time", comm());
                 }
                 region_begin("Sparse Cyclic Shift Time", comm());
-                if (!early) blk->shiftCSR_no_flip(s_src, s_dst, sparse_ring, incoming, comm());
-                else if (sddmm) blk->shift_values(s_src, s_dst, sparse_ring, incoming, comm());
+                if (!early) blk->shiftCSR_no_flip(s_src, s_dst, sparse_ring_comm, incoming, comm());
+                else if (sddmm) blk->shift_values(s_src, s_dst, sparse_ring_comm, incoming, comm());
                 region_end("Sparse Cyclic Shift Time", comm());
                 ride.swapActive();
                 blk->shift_commit(incoming);
@@ -187,6 +235,7 @@ public:
             }
         }
         ride.sync_active();
+        }
 
         if (sddmm) {
             region_begin("Computation Time", compute());

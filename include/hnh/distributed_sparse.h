@@ -145,6 +145,14 @@ protected:
     std::map<std::pair<hnh::Comm *, size_t>, std::unique_ptr<hnh::PeerRing>> peer_rings_;
     bool peer_ring_broken_ = false;
     hnh::PeerRing *peer_ring(std::shared_ptr<hnh::Comm> world, size_t bytes);
+    // the same for a riding CSR block: the ring pushes straight into the next rank's passive CSRHandle
+    std::map<std::pair<hnh::Comm *, CSRLocal *>, std::unique_ptr<hnh::PeerRing>> sparse_rings_;
+    hnh::PeerRing *sparse_ring(std::shared_ptr<hnh::Comm> world, CSRLocal *blk);
+    // One ring step of a CSR block over a copy-engine ring.  Call early() before the kernel that uses
+    // the block (ships what the kernel does not write), late() after it (ships the rest, publishes,
+    // commits).  `values_written`: the kernel accumulates into the block's values (SDDMM).
+    void sparse_push_early(hnh::PeerRing &pr, CSRLocal &blk, bool values_written);
+    void sparse_push_late(hnh::PeerRing &pr, CSRLocal &blk, bool values_written, bool early_done, int64_t incoming);
 
     // Driver of a dense ring over `world` (+1 direction, `steps` = world size):
     //   step t: body(t, riding) on the compute stream, then the riding matrix moves one rank on.
@@ -231,7 +239,41 @@ void Distributed_Sparse::ring_dense(DenseMatrix &home, std::shared_ptr<hnh::Comm
         rt.chain(comm(), compute());
         return;
     }
-    // strictly alternating kernel / shift on two buffers (output rides, or overlap disabled)
+    // output rides (or overlap disabled): kernel and shift strictly alternate
+    hnh::PeerRing *pro = (!riding_is_input && overlap && hnh::PeerRing::all_shifts()) ? peer_ring(world_ptr, bytes) : nullptr;
+    if (pro) {
+        // copy engines instead of NCCL p2p (which gets few channels per peer at 8 ranks): the
+        // accumulating shard hops through the ring slots and is copied home at the end
+        for (int t = 0; t < steps; t++) {
+            const int k = t & 1;
+            if (t >= 1) {
+                pro->expect_arrival(k);
+                pro->wait_arrival(k, compute());
+            }
+            region_begin(compute_key, compute());
+            if (t == 0) {
+                body(t, home);
+            } else {
+                DenseMatrix shard = DenseMatrix::view((double *)pro->slot(k), home.rows(), home.cols());
+                body(t, shard);
+            }
+            region_end(compute_key, compute());
+            rt.chain(compute(), comm());
+            region_begin(shift_key, comm());
+            pro->push((t + 1) & 1, t == 0 ? (const void *)home.data() : pro->slot(k), bytes, comm());
+            if (t >= 1) pro->release(k, comm());
+            region_end(shift_key, comm());
+        }
+        const int kf = steps & 1;
+        pro->expect_arrival(kf);
+        region_begin(shift_key, comm());
+        pro->wait_arrival(kf, comm());
+        hnh::cuda_check(cudaMemcpyAsync(home.data(), pro->slot(kf), bytes, cudaMemcpyDeviceToDevice, comm()), "ring copy-back");
+        pro->release(kf, comm());
+        region_end(shift_key, comm());
+        rt.chain(comm(), compute());
+        return;
+    }
     BufferPair pair(&home);
     for (int t = 0; t < steps; t++) {
         region_begin(compute_key, compute());

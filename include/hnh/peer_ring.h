@@ -18,9 +18,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <array>
 #include <cstddef>
 #include <cstdint>
 #include <memory>
+#include <vector>
 
 #include "hnh/comm.h"
 
@@ -31,6 +33,13 @@ public:
     // Collective over `ring` (size >= 2): allocates the slots, exchanges IPC handles.
     // Throws Error if peer mapping is not possible (the caller then falls back to NCCL).
     PeerRing(std::shared_ptr<Comm> ring, size_t slot_bytes);
+    // Same protocol on buffers the caller owns (e.g. the two CSRHandle buffers of a CSRLocal):
+    // external[i] = {local pointer of logical buffer i in slot 0, ... in slot 1}; every pointer must be
+    // the base of a cudaMalloc allocation (at most 4 logical buffers).  Collective over `ring`.
+    // `resident_slot`: the slot that already holds live data on every rank when the ring is built (a
+    // CSRLocal's active handle); it is accounted for as if it had been pushed once, so that the first
+    // real push into it waits until the downstream rank has consumed its resident block.
+    PeerRing(std::shared_ptr<Comm> ring, const std::vector<std::array<void *, 2>> &external, int resident_slot);
     ~PeerRing();
     PeerRing(const PeerRing &) = delete;
     PeerRing &operator=(const PeerRing &) = delete;
@@ -41,6 +50,12 @@ public:
     // enqueue on `s`: wait until downstream slot k may be overwritten, copy `bytes` from local
     // `src` into it, then tell the downstream rank that the shard has landed
     void push(int k, const void *src, size_t bytes, cudaStream_t s);
+    // the same in pieces: begin_push waits until downstream slot k may be overwritten, the caller then
+    // copies into dst_ptr(i, k) with plain cudaMemcpyAsync on the same stream (any number of pieces, on
+    // either side of a kernel), end_push publishes the arrival
+    void begin_push(int k, cudaStream_t s);
+    void *dst_ptr(int i, int k) const { return dst_[(size_t)i][(size_t)k]; }
+    void end_push(int k, cudaStream_t s);
     // register that the caller is about to consume the next shard of my slot k (call once per
     // shard), then make stream(s) wait for its arrival
     void expect_arrival(int k);
@@ -48,7 +63,8 @@ public:
     // enqueue on `s`: tell the upstream rank that my slot k has been consumed
     void release(int k, cudaStream_t s);
 
-    static bool enabled();  // HNH_RING != "nccl"
+    static bool enabled();      // HNH_RING != "nccl"
+    static bool all_shifts();   // also use copy-engine rings where the riding data is an output / a CSR block
 
 private:
     struct Flags {
@@ -57,12 +73,14 @@ private:
     };
     std::shared_ptr<Comm> ring_;
     size_t bytes_;
-    void *slot_[2] = {nullptr, nullptr};
+    void *slot_[2] = {nullptr, nullptr};  // owned slots (first constructor only)
+    bool owns_slots_ = false;
     Flags *flags_ = nullptr;            // mine
-    void *dst_slot_[2] = {nullptr, nullptr};
+    std::vector<std::array<void *, 2>> dst_;  // downstream's buffers, IPC-mapped
     Flags *dst_flags_ = nullptr;        // downstream's, IPC-mapped
     Flags *src_flags_ = nullptr;        // upstream's, IPC-mapped
-    bool opened_[4] = {false, false, false, false};
+    bool src_flags_opened_ = false;
+    void connect(const std::vector<std::array<void *, 2>> &local, int resident_slot);
     uint32_t pushed_[2] = {0, 0};    // shards I pushed into downstream slot k
     uint32_t expected_[2] = {0, 0};  // arrivals into my slot k that have been claimed
     uint32_t consumed_[2] = {0, 0};  // shards of my slot k that I have released

@@ -46,8 +46,11 @@ def test_all_operations_match_reference(nproc):
         want, src = U.reference_for(c, nproc)
         if want is None:
             continue
-        U.compare_layout(got[c["name"]], want, c["alg"])
-        worst = max(worst, U.compare_ops(got[c["name"]], want, c["script"]))
+        try:
+            U.compare_layout(got[c["name"]], want, c["alg"])
+            worst = max(worst, U.compare_ops(got[c["name"]], want, c["script"]))
+        except AssertionError as e:
+            raise AssertionError(f"case {c['name']} (p={nproc}, reference from {src}): {e}") from e
         checked += 1
     assert checked > 0, "neither oracle/_ref/libhnh_ref.so nor tests/golden files are available"
     print(f"nproc={nproc}: {checked} cases, worst relative error {worst:.2e}")
