@@ -144,6 +144,7 @@ ABI.update({
     "hnhd_alg_op": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int]),
     "hnhd_timer_start": (C.c_int, []),
     "hnhd_timer_stop": (C.c_int, [C.POINTER(C.c_double)]),
+    "hnhd_als_residuals": (C.c_int, [_P, C.c_int, _P]),
     "hnhd_benchmark_algorithm": (C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p,
                                            C.c_int, C.c_int, C.c_char_p, _SZ]),
 })

@@ -8,6 +8,7 @@
 #include "hnh/15D_sparse_shift.hpp"
 #include "hnh/25D_cannon_dense.hpp"
 #include "hnh/25D_cannon_sparse.hpp"
+#include "hnh/als_conjugate_gradients.h"
 #include "hnh/benchmark_dist.hpp"
 #include "hnh/distributed_sparse.h"
 #include "hnh_b200.h"
@@ -301,6 +302,20 @@ int hnhd_benchmark_algorithm(hnhd_spmat_t *S, const char *algorithm_name, const 
         n = json_out ? copy_json(j, json_out, capacity) : 0;
     });
     return rc ? rc : n;
+}
+
+int hnhd_als_residuals(hnhd_alg_t *a, int steps, double *out2) {
+    return guarded([&] {
+        if (!a || !out2) throw hnh::Error(HNH_E_INVALID, "null argument");
+        Distributed_ALS als(a->alg.get(), true);
+        als.initializeEmbeddings();
+        out2[0] = als.computeResidual();
+        for (int i = 0; i < steps; i++) {
+            als.cg_optimizer(Amat, 10);
+            als.cg_optimizer(Bmat, 10);
+        }
+        out2[1] = als.computeResidual();
+    });
 }
 
 }  // extern "C"

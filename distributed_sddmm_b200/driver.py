@@ -259,6 +259,12 @@ class Algorithm:
     def reset_timers(self):
         check(lib().hnhd_alg_reset_timers(self.h), "reset_timers")
 
+    def als_residuals(self, steps=1):
+        """(residual before, residual after) `steps` rounds of ALS-CG on an artificial ground truth."""
+        out = (C.c_double * 2)()
+        check(lib().hnhd_als_residuals(self.h, steps, out), "hnhd_als_residuals")
+        return out[0], out[1]
+
     def blocks(self, which="S"):
         """Host copies of the local CSR blocks: list of None | dict(rows, cols, transpose, rowStart, col_idx,
         row_idx, values)."""

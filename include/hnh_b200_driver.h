@@ -147,6 +147,11 @@ int hnhd_benchmark_algorithm(hnhd_spmat_t *S, const char *algorithm_name, const 
                              int fused, int R, int c, const char *app, int trials, int warmup,
                              char *json_out, size_t capacity);
 
+/* Distributed_ALS on `alg` (als_conjugate_gradients.cpp): artificial ground truth, initializeEmbeddings(),
+ * residual, `steps` alternating cg_optimizer(Amat, 10) / cg_optimizer(Bmat, 10) rounds, residual again.
+ * out2 = {residual before, residual after} (world-reduced, identical on every rank).  Collective. */
+int hnhd_als_residuals(hnhd_alg_t *alg, int steps, double *out2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,6 +136,8 @@ def main():
                     raise ValueError(op)
                 out[f"op{t}_A"], out[f"op{t}_B"], out[f"op{t}_values"] = A.to_host(), B.to_host(), vals
             out["perf"] = json.dumps(alg.perf())
+            if case.get("als"):
+                out["als"] = np.array(alg.als_residuals(1))
         out["info"] = json.dumps(alg.info())
         np.savez(os.path.join(outdir, f"{name}_rank{rank}.npz"), **out)
         del alg, S

@@ -136,3 +136,6 @@ def test_als_cg_reduces_residual(world):
     S = D.SpmatLocal.load_er(10, 8, SEED)
     rec = D.benchmark_algorithm(S, "15d_fusion2", R=16, c=1, fused=True, app="als", trials=1, warmup=0)
     assert rec["overall_throughput"] > 0
+    for name in ALGS:
+        before, after = D.Algorithm(name, S, 16, 1).als_residuals(1)
+        assert np.isfinite([before, after]).all() and after < before, (name, before, after)

@@ -6,6 +6,7 @@ How the ranks are mapped: with at least `nproc` GPUs each rank gets its own GPU 
 shifts / collectives are NCCL; on a one-GPU box the ranks are processes sharing cuda:0 and the
 External transport (gloo, device buffers staged through pinned memory) carries the messages, so
 the algorithm code under test is identical."""
+import numpy as np
 import pytest
 import torch
 
@@ -14,15 +15,15 @@ from tests import mp_util as U
 pytestmark = pytest.mark.gpu
 
 CASES = {
-    2: [U.case("15d_fusion1", 1, 8, 7, 5), U.case("15d_fusion1", 2, 8, 7, 5), U.case("15d_fusion2", 1, 8, 7, 5),
+    2: [dict(U.case("15d_fusion1", 1, 8, 7, 5), als=1), U.case("15d_fusion1", 2, 8, 7, 5), U.case("15d_fusion2", 1, 8, 7, 5),
         U.case("15d_fusion2", 2, 8, 7, 5), U.case("15d_sparse", 1, 8, 7, 5), U.case("15d_sparse", 2, 8, 7, 5),
         U.case("25d_sparse_replicate", 2, 8, 7, 5),
         U.case("15d_fusion2", 1, 8, 7, 5, n=101), U.case("15d_sparse", 1, 8, 7, 5, n=101),  # padded trailing blocks
         # wide factors (the r = 128 kernels); too large for a golden file: needs oracle/_ref
         U.case("15d_fusion2", 1, 128, 9, 6, name="nogolden_fusion2_r128"),
         U.case("15d_fusion1", 1, 128, 9, 6, name="nogolden_fusion1_r128")],
-    4: [U.case("15d_fusion1", 2, 8, 7, 5), U.case("15d_fusion2", 1, 16, 7, 5), U.case("15d_fusion2", 4, 8, 7, 5),
-        U.case("15d_sparse", 1, 8, 7, 5), U.case("15d_sparse", 2, 32, 7, 5), U.case("25d_dense_replicate", 1, 8, 7, 5),
+    4: [U.case("15d_fusion1", 2, 8, 7, 5), dict(U.case("15d_fusion2", 1, 16, 7, 5), als=1), U.case("15d_fusion2", 4, 8, 7, 5),
+        U.case("15d_sparse", 1, 8, 7, 5), dict(U.case("15d_sparse", 2, 32, 7, 5), als=1), dict(U.case("25d_dense_replicate", 1, 8, 7, 5), als=1),
         U.case("25d_sparse_replicate", 1, 8, 7, 5),
         U.case("15d_fusion1", 2, 8, 7, 5, n=99), U.case("25d_dense_replicate", 1, 8, 7, 5, n=99)],
     8: [U.case("15d_fusion1", 2, 8, 8, 5), U.case("15d_fusion2", 1, 8, 8, 5), U.case("15d_sparse", 1, 32, 8, 5),
@@ -53,4 +54,11 @@ def test_all_operations_match_reference(nproc):
             raise AssertionError(f"case {c['name']} (p={nproc}, reference from {src}): {e}") from e
         checked += 1
     assert checked > 0, "neither oracle/_ref/libhnh_ref.so nor tests/golden files are available"
+    # ALS-CG (the config-5 caller) on the same algorithm objects: runs on every layout, all ranks agree on
+    # the world-reduced residual, and one alternating round shrinks it
+    for c in cases:
+        if c.get("als"):
+            res = [r["als"] for r in got[c["name"]]]
+            assert all(np.array_equal(res[0], x) for x in res), (c["name"], res)
+            assert np.isfinite(res[0]).all() and res[0][1] < res[0][0], (c["name"], res[0])
     print(f"nproc={nproc}: {checked} cases, worst relative error {worst:.2e}")
