@@ -214,7 +214,7 @@ static bool tma_default(bool fused, int r, bool overwrite_out) {
 // 256-bit loads (VW=4) need 32-byte aligned operand rows; 128-bit (VW=2) need 16.
 #define HNH_DISPATCH_R(r, WIDE, CALL4, CALL2, FALLBACK)          \
     switch (r) {                                                  \
-        case 4:   if (WIDE) { CALL2(4, 2, 2, 2); } else { CALL2(4, 2, 2, 2); } break;    \
+        case 4:   CALL2(4, 2, 2, 2); break; /* a 4-double row is one 32-byte sector: 128-bit loads either way */ \
         case 8:   if (WIDE) { CALL4(8, 2, 4, 2); } else { CALL2(8, 4, 2, 4); } break;    \
         case 16:  if (WIDE) { CALL4(16, 4, 4, 4); } else { CALL2(16, 8, 2, 4); } break;  \
         case 32:  if (WIDE) { CALL4(32, 8, 4, 4); } else { CALL2(32, 16, 2, 4); } break; \

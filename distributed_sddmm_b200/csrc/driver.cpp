@@ -55,7 +55,6 @@ int copy_json(const json &j, char *out, size_t capacity) {
     return (int)s.size();
 }
 
-hnh::DeviceBuffer<double> *dummy = nullptr;
 cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
 
 }  // namespace

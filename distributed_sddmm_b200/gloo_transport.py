@@ -69,8 +69,7 @@ class GlooTransport:
             if len(ranks) == 1:
                 out.copy_(s)
             else:
-                dist.all_gather_into_tensor(out, s, group=g) if hasattr(dist, "all_gather_into_tensor") and False else \
-                    self._ag_list(out, s, g, len(ranks), nbytes)
+                self._ag_list(out, s, g, len(ranks), nbytes)
         return self._guard(run)
 
     @staticmethod
