@@ -200,6 +200,19 @@ int launch_tma(const int64_t *rowStart, const int64_t *col_idx, double *values, 
 // (profiles/r01_tma_vs_direct.md): SDDMM gains 2-8 % with TMA staging at r = 128 and 256; the fused
 // kernel gains 9 % at r = 256 (BETA0) but loses 13 % at r = 128 (the per-tile barrier makes the 8 warps
 // of a CTA wait for the longest of their rows).  HNH_TMA=0 / 1 forces one or the other everywhere.
+template <int R, bool FUSED>
+int launch_tma_warp(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows, const double *X,
+                    const double *Y, double *Out, bool bv, bool bo, cudaStream_t st) {
+    int grid;
+    auto k = bv ? (bo ? tma_warp_kernel<R, 4, FUSED, true, true> : tma_warp_kernel<R, 4, FUSED, true, false>)
+                : (bo ? tma_warp_kernel<R, 4, FUSED, false, true> : tma_warp_kernel<R, 4, FUSED, false, false>);
+    int rc = grid_for(k, kBlock, 8, rows, &grid);
+    if (rc) return rc;
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "tma_warp_kernel launch");
+}
+
 static bool tma_default(bool fused, int r, bool overwrite_out) {
     static int v = -2;
     if (v == -2) {
@@ -273,6 +286,10 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         }                                                                                    \
     }
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
+    if ((flags & HNH_FLAG_TMA_WARP) && a32 && (r == 128 || r == 256) && !(flags & HNH_FLAG_FORCE_GENERIC)) {
+        return r == 128 ? launch_tma_warp<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st)
+                        : launch_tma_warp<256, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st);
+    }
     if (((flags & HNH_FLAG_TMA_STAGE) || (tma_default(false, r, beta0) && !(flags & HNH_FLAG_FORCE_DIRECT))) && a32 &&
         (r == 128 || r == 256) && !(flags & HNH_FLAG_FORCE_GENERIC)) {
         return r == 128 ? launch_tma<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st)
@@ -405,6 +422,10 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
     // in place (Out == X) is not offered with TMA staging: the next tile of X is prefetched while
     // the current one is still being written
+    if ((flags & HNH_FLAG_TMA_WARP) && a32 && (r == 128 || r == 256) && X != Out && !(flags & HNH_FLAG_FORCE_GENERIC)) {
+        return r == 128 ? launch_tma_warp<128, true>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)
+                        : launch_tma_warp<256, true>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st);
+    }
     if (((flags & HNH_FLAG_TMA_STAGE) || (tma_default(true, r, bo) && !(flags & HNH_FLAG_FORCE_DIRECT))) && a32 &&
         (r == 128 || r == 256) && X != Out && !(flags & HNH_FLAG_FORCE_GENERIC)) {
         return r == 128 ? launch_tma<128, true>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)

@@ -466,6 +466,114 @@ tma_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__
     }
 }
 
+// Per-warp variant (HNH_FLAG_TMA_WARP; experimental, never the default): every warp owns two
+// row-sized shared-memory slots and two mbarriers and prefetches the X row of its NEXT CSR row with
+// its own bulk copy while it gathers for the current one.  No block-wide barrier, so the warps of a
+// CTA do not wait for each other's longest row (the cost that makes tma_row_kernel lose at r = 128
+// for the fused kernel, profiles/r01_tma_vs_direct.md).
+template <int R, int UN, bool FUSED, bool BV, bool BO>
+__global__ void __launch_bounds__(256)
+tma_warp_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx, double *__restrict__ values,
+                int64_t rows, const double *X, const double *__restrict__ Y, double *Out) {
+    constexpr int G = 32, VW = 4, NW = 8;
+    constexpr int NV = R / (G * VW);
+    static_assert(NV * G * VW == R, "R must be a multiple of 128");
+    __shared__ alignas(128) double xs[NW][2][R];
+    __shared__ alignas(8) uint64_t bars[NW][2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned gmask = 0xffffffffu;
+    const int64_t stride = (int64_t)gridDim.x * NW;
+    int64_t row = (int64_t)blockIdx.x * NW + w;
+    if (lane == 0) {
+        mbar_init(&bars[w][0], 1);
+        mbar_init(&bars[w][1], 1);
+    }
+    __syncwarp();
+    unsigned par0 = 0, par1 = 0;
+    int slot = 0;
+    if (lane == 0 && row < rows) bulk_load(&xs[w][0][0], X + row * R, (unsigned)(R * sizeof(double)), &bars[w][0]);
+    for (; row < rows; row += stride) {
+        const int64_t next = row + stride;
+        if (lane == 0 && next < rows)
+            bulk_load(&xs[w][slot ^ 1][0], X + next * R, (unsigned)(R * sizeof(double)), &bars[w][slot ^ 1]);
+        if (slot == 0) { mbar_wait(&bars[w][0], par0); par0 ^= 1; }
+        else { mbar_wait(&bars[w][1], par1); par1 ^= 1; }
+        double x[NV][VW];
+#pragma unroll
+        for (int v = 0; v < NV; v++)
+#pragma unroll
+            for (int q = 0; q < VW; q++) x[v][q] = xs[w][slot][(v * G + lane) * VW + q];
+        __syncwarp();  // the slot may be refilled from the next iteration on
+        slot ^= 1;
+        const int64_t s = ld_stream_i64(rowStart + row);
+        const int64_t e = ld_stream_i64(rowStart + row + 1);
+        if (FUSED && !BO && s == e) continue;
+        double acc[NV][VW];
+        if (FUSED) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) {
+                if (BO) {
+#pragma unroll
+                    for (int q = 0; q < VW; q++) acc[v][q] = 0.0;
+                } else {
+                    ld_rw<VW>(acc[v], Out + row * R + (v * G + lane) * VW);
+                }
+            }
+        }
+        for (int64_t j = s; j < e; j += G) {
+            const int cnt = (e - j < G) ? (int)(e - j) : G;
+            int64_t mycol = 0;
+            double myval = 0.0;
+            if (lane < cnt) {
+                mycol = ld_stream_i64(col_idx + j + lane);
+                if (!BV) myval = values[j + lane];
+            }
+            for (int k0 = 0; k0 < cnt; k0 += UN) {
+                double y[UN][NV][VW];
+                double vold[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const int k = k0 + u;
+                    const int src = k < G ? k : G - 1;
+                    const int64_t c = __shfl_sync(gmask, mycol, src, G);
+                    vold[u] = __shfl_sync(gmask, myval, src, G);
+                    if (k < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++) ld_gather<VW>(y[u][v], Y + c * R + (v * G + lane) * VW);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int q = 0; q < VW; q++) y[u][v][q] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int v = 0; v < NV; v++)
+#pragma unroll
+                        for (int q = 0; q < VW; q++) d = fma(x[v][q], y[u][v][q], d);
+                    d = group_allreduce<G>(d, gmask);
+                    const double vnew = vold[u] + d;
+                    if (lane == k0 + u) myval = vnew;
+                    if (FUSED && k0 + u < cnt) {
+#pragma unroll
+                        for (int v = 0; v < NV; v++)
+#pragma unroll
+                            for (int q = 0; q < VW; q++) acc[v][q] = fma(vnew, y[u][v][q], acc[v][q]);
+                    }
+                }
+            }
+            if (lane < cnt) values[j + lane] = myval;
+        }
+        if (FUSED) {
+#pragma unroll
+            for (int v = 0; v < NV; v++) st_rw<VW>(Out + row * R + (v * G + lane) * VW, acc[v]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ small-r kernels ------
 // For narrow factors (r <= 32) a row is too short to feed a whole warp, so the G = GK*GN lanes
 // that own a CSR row are laid out in two dimensions: GK lanes split the r columns (VW doubles

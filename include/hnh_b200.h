@@ -53,6 +53,8 @@ extern "C" {
  * otherwise); HNH_FLAG_FORCE_DIRECT or env HNH_TMA=0 force the direct-load kernels, HNH_TMA=1 the
  * TMA-staged ones. */
 #define HNH_FLAG_TMA_STAGE 64
+/* experimental: per-warp TMA slots (no block barrier); never selected automatically */
+#define HNH_FLAG_TMA_WARP 128
 
 /* ABI / build identification. */
 int hnh_abi_version(void);

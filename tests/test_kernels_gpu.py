@@ -284,3 +284,22 @@ def test_tma_staged_variants_match_oracle(hnh, R):
     vref0, oref0 = orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), A, B, np.zeros((M, R)))
     v, o = gu.run_fused(csr, v0, A, B, O0, flags=TMA | BETA0)
     assert rel_err(v, vref0) < RTOL and rel_err(o, oref0) < RTOL
+
+
+@pytest.mark.parametrize("R", [128, 256])
+def test_tma_per_warp_variant_matches_direct(hnh, R):
+    """HNH_FLAG_TMA_WARP (experimental, never selected automatically): per-warp bulk-copy slots."""
+    WARP, DIRECT, BETA0 = 128, 2, 4
+    rng = np.random.default_rng(22)
+    M, N = 2051, 901
+    r = rng.integers(0, M, 30000).astype(np.uint64)
+    c = rng.integers(0, N, 30000).astype(np.uint64)
+    order = np.lexsort((r, c))
+    csr = orc.coo_to_csr(M, N, r[order], c[order], np.ones(len(r)))
+    A, B = rng.uniform(-1, 1, (M, R)), rng.uniform(-1, 1, (N, R))
+    v0, O0 = rng.uniform(-1, 1, csr.nnz), rng.uniform(-1, 1, (M, R))
+    for extra in (0, BETA0):
+        assert np.array_equal(gu.run_sddmm(csr, A, B, v0, flags=WARP | extra), gu.run_sddmm(csr, A, B, v0, flags=DIRECT | extra))
+        v, o = gu.run_fused(csr, v0, A, B, O0, flags=WARP | extra)
+        vd, od = gu.run_fused(csr, v0, A, B, O0, flags=DIRECT | extra)
+        assert np.array_equal(v, vd) and np.array_equal(o, od)
