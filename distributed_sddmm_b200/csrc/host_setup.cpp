@@ -7,6 +7,7 @@
 // used: both are plain C++ here.
 #include "hnh_b200.h"
 #include "launch.h"
+#include "host_sort.h"
 
 #include <algorithm>
 #include <cstring>
@@ -93,23 +94,20 @@ int hnh_coo_to_csr_host(int64_t rows, int64_t cols, int64_t nnz, const uint64_t 
     const int64_t out_cols = transpose ? rows : cols;
     const uint64_t *sr = transpose ? c : r;  // stored row
     const uint64_t *sc = transpose ? r : c;  // stored col
-    std::memset(rowStart, 0, sizeof(int64_t) * (size_t)(out_rows + 1));
-    for (int64_t i = 0; i < nnz; i++) {
-        if (sr[i] >= (uint64_t)out_rows || sc[i] >= (uint64_t)out_cols)
-            return hnh::set_error(HNH_E_INVALID,
-                                  "hnh_coo_to_csr_host: coordinate (%llu,%llu) outside %lld x %lld",
-                                  (unsigned long long)r[i], (unsigned long long)c[i],
-                                  (long long)rows, (long long)cols);
-        rowStart[sr[i] + 1]++;
-    }
-    for (int64_t i = 0; i < out_rows; i++) rowStart[i + 1] += rowStart[i];
-    std::vector<int64_t> cursor(rowStart, rowStart + out_rows);
-    for (int64_t i = 0; i < nnz; i++) {
-        const int64_t p = cursor[sr[i]]++;
-        col_idx[p] = (int64_t)sc[i];
-        values[p] = v[i];
-        if (row_idx) row_idx[p] = (int64_t)sr[i];
-    }
+    bool col_bad = false;
+#pragma omp parallel for reduction(|| : col_bad)
+    for (int64_t i = 0; i < nnz; i++) col_bad = col_bad || sc[i] >= (uint64_t)out_cols;
+    const bool ok = !col_bad && hnh::stable_counting_sort(
+        nnz, out_rows, [&](int64_t i) { return sr[i] < (uint64_t)out_rows ? (int64_t)sr[i] : (int64_t)-1; },
+        [&](int64_t i, int64_t p) {
+            col_idx[p] = (int64_t)sc[i];
+            values[p] = v[i];
+            if (row_idx) row_idx[p] = (int64_t)sr[i];
+        },
+        rowStart);
+    if (!ok)
+        return hnh::set_error(HNH_E_INVALID, "hnh_coo_to_csr_host: a coordinate lies outside the %lld x %lld block",
+                              (long long)rows, (long long)cols);
     return HNH_OK;
 }
 

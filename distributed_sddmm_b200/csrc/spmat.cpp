@@ -9,6 +9,7 @@
 #include <sstream>
 
 #include "hnh_b200.h"
+#include "host_sort.h"
 
 using hnh::abi_check;
 using hnh::cuda_check;
@@ -30,19 +31,28 @@ CSRLocal::CSRLocal(int64_t rows_in, int64_t cols_in, int64_t max_nnz_in, spcoord
     : rows(tr ? cols_in : rows_in), cols(tr ? rows_in : cols_in), max_nnz(max_nnz_in), num_coords(n),
       transpose(tr), active(0), buffer(new CSRHandle[2]) {
     if (n > max_nnz) throw hnh::Error(HNH_E_INVALID, "CSRLocal: num_coords > max_nnz");
-    vector<uint64_t> r((size_t)n), c((size_t)n);
-    vector<double> v((size_t)n);
-#pragma omp parallel for
-    for (int64_t i = 0; i < n; i++) {
-        r[i] = coords[i].r;
-        c[i] = coords[i].c;
-        v[i] = coords[i].value;
-    }
     vector<int64_t> rowStart((size_t)rows + 1), col_idx((size_t)std::max<int64_t>(n, 1)), row_idx((size_t)std::max<int64_t>(n, 1));
     vector<double> values((size_t)std::max<int64_t>(n, 1));
-    abi_check(hnh_coo_to_csr_host(rows_in, cols_in, n, r.data(), c.data(), v.data(), tr ? 1 : 0, rowStart.data(),
-                                  col_idx.data(), row_idx.data(), values.data()),
-              "COO->CSR");
+    {
+        // COO -> CSR straight from the tuples (stable counting sort by stored row)
+        const uint64_t lim_r = (uint64_t)rows, lim_c = (uint64_t)cols;
+        bool col_bad = false;
+#pragma omp parallel for reduction(|| : col_bad)
+        for (int64_t i = 0; i < n; i++) col_bad = col_bad || (tr ? coords[i].r : coords[i].c) >= lim_c;
+        const bool ok = !col_bad && hnh::stable_counting_sort(
+            n, rows,
+            [&](int64_t i) {
+                const uint64_t sr = tr ? coords[i].c : coords[i].r;
+                return sr < lim_r ? (int64_t)sr : (int64_t)-1;
+            },
+            [&](int64_t i, int64_t p) {
+                col_idx[p] = (int64_t)(tr ? coords[i].r : coords[i].c);
+                row_idx[p] = (int64_t)(tr ? coords[i].c : coords[i].r);
+                values[p] = coords[i].value;
+            },
+            rowStart.data());
+        if (!ok) throw hnh::Error(HNH_E_INVALID, "CSRLocal: a coordinate lies outside the block");
+    }
 #pragma omp parallel for
     for (int64_t i = 0; i < n; i++) {
         coords[i].r = (uint64_t)row_idx[i];
@@ -225,23 +235,25 @@ SpmatLocal *SpmatLocal::redistribute_nonzeros(NonzeroDistribution *dist, bool tr
     vector<int> owner((size_t)n);
 #pragma omp parallel for
     for (int64_t i = 0; i < n; i++) owner[i] = dist->getOwner((int64_t)coords[i].r, (int64_t)coords[i].c, transpose);
+    // stable parallel counting sort of the tuples into per-destination segments
     vector<size_t> send_tuples((size_t)p, 0);
-    for (int64_t i = 0; i < n; i++) {
-        if (owner[i] < 0 || owner[i] >= p) throw hnh::Error(HNH_E_INVALID, "redistribute_nonzeros: owner out of range");
-        send_tuples[owner[i]]++;
-    }
     vector<size_t> send_off((size_t)p + 1, 0);
-    for (int i = 0; i < p; i++) send_off[i + 1] = send_off[i] + send_tuples[i];
     vector<spcoord_t> sendbuf((size_t)n);
     {
-        vector<size_t> cursor(send_off.begin(), send_off.end() - 1);
-        for (int64_t i = 0; i < n; i++) {
-            spcoord_t t;
-            t.r = transpose ? coords[i].c : coords[i].r;
-            t.c = transpose ? coords[i].r : coords[i].c;
-            t.value = coords[i].value;
-            sendbuf[cursor[owner[i]]++] = t;
-        }
+        vector<int64_t> starts((size_t)p + 1, 0);
+        const bool ok = hnh::stable_counting_sort(
+            n, p, [&](int64_t i) { return (int64_t)owner[i]; },
+            [&](int64_t i, int64_t pos) {
+                spcoord_t t;
+                t.r = transpose ? coords[i].c : coords[i].r;
+                t.c = transpose ? coords[i].r : coords[i].c;
+                t.value = coords[i].value;
+                sendbuf[(size_t)pos] = t;
+            },
+            starts.data());
+        if (!ok) throw hnh::Error(HNH_E_INVALID, "redistribute_nonzeros: owner out of range");
+        for (int i = 0; i <= p; i++) send_off[(size_t)i] = (size_t)starts[(size_t)i];
+        for (int i = 0; i < p; i++) send_tuples[(size_t)i] = send_off[(size_t)i + 1] - send_off[(size_t)i];
     }
     vector<int>().swap(owner);
 
@@ -270,8 +282,8 @@ SpmatLocal *SpmatLocal::redistribute_nonzeros(NonzeroDistribution *dist, bool tr
     result->N = transpose ? oldM : oldN;
     result->dist_nnz = dist_nnz;
     result->initialized = true;
+    __gnu_parallel::sort(received.begin(), received.end(), column_major);
     result->coords.swap(received);
-    __gnu_parallel::sort(result->coords.begin(), result->coords.end(), column_major);
     return result;
 }
 
