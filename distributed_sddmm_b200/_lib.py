@@ -45,6 +45,21 @@ ABI = {
 }
 
 
+def _preload_bundled_nccl():
+    """libhnh_b200.so needs `libnccl.so.2`.  When PyTorch shares the process it brings its own, newer
+    NCCL under the same soname; whichever copy is mapped first serves both.  Map PyTorch's copy first
+    (when there is one) so that a later `import torch` still finds every symbol it was built against."""
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def lib():
     """Load libhnh_b200.so (built in-tree by build.py).  Raises LibraryMissing loudly when it
     has not been built -- the product has no fallback path."""
@@ -55,6 +70,7 @@ def lib():
             raise LibraryMissing(
                 f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
                 " (nvcc, sm_100a).  distributed_sddmm_b200 has no CPU fallback.")
+        _preload_bundled_nccl()
         L = C.CDLL(path)
         for name, (res, args) in ABI.items():
             fn = getattr(L, name)
@@ -109,6 +125,7 @@ ABI.update({
     "hnhd_barrier": (C.c_int, []),
     "hnhd_device_synchronize": (C.c_int, []),
     "hnhd_spmat_load_er": (C.c_int, [C.c_int, C.c_int, C.c_uint64, _PP]),
+    "hnhd_spmat_load_file": (C.c_int, [C.c_char_p, _PP]),
     "hnhd_spmat_from_tuples": (C.c_int, [C.c_uint64, C.c_uint64, _P, _P, _P, _I64, _PP]),
     "hnhd_spmat_info": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                   C.POINTER(C.c_int64)]),

@@ -90,6 +90,14 @@ int hnhd_spmat_load_er(int logM, int nnz_per_row, uint64_t seed, hnhd_spmat_t **
         *out = s.release();
     });
 }
+int hnhd_spmat_load_file(const char *filename, hnhd_spmat_t **out) {
+    return guarded([&] {
+        if (!filename || !out) throw hnh::Error(HNH_E_INVALID, "null argument");
+        std::unique_ptr<hnhd_spmat> s(new hnhd_spmat);
+        s->m.loadTuples(true, -1, -1, filename);
+        *out = s.release();
+    });
+}
 int hnhd_spmat_from_tuples(uint64_t M, uint64_t N, const uint64_t *rows, const uint64_t *cols, const double *vals,
                            int64_t n_local, hnhd_spmat_t **out) {
     return guarded([&] {

@@ -88,6 +88,12 @@ class SpmatLocal:
         return cls(h)
 
     @classmethod
+    def load_file(cls, filename: str):
+        h = C.c_void_p()
+        check(lib().hnhd_spmat_load_file(filename.encode(), C.byref(h)), "hnhd_spmat_load_file")
+        return cls(h)
+
+    @classmethod
     def from_tuples(cls, M, N, rows, cols, vals):
         rows = np.ascontiguousarray(rows, np.uint64)
         cols = np.ascontiguousarray(cols, np.uint64)

@@ -57,6 +57,9 @@ typedef struct hnhd_spmat hnhd_spmat_t;
 /* SpmatLocal::loadTuples(false, logM, nnz_per_row, "") (SpmatLocal.hpp:467-533) with the
  * repo's seeded Erdos-Renyi generator; every rank generates its 1-D row slice. */
 int hnhd_spmat_load_er(int logM, int nnz_per_row, uint64_t seed, hnhd_spmat_t **out);
+/* SpmatLocal::loadTuples(true, -1, -1, filename): MatrixMarket coordinate file (general / symmetric, real /
+ * integer / pattern); every rank keeps a share of the entries (SpmatLocal.hpp:479-491 reads with CombBLAS). */
+int hnhd_spmat_load_file(const char *filename, hnhd_spmat_t **out);
 /* Arbitrary local tuples of a global M x N matrix (any distribution over the ranks). */
 int hnhd_spmat_from_tuples(uint64_t M, uint64_t N, const uint64_t *rows, const uint64_t *cols,
                            const double *vals, int64_t n_local, hnhd_spmat_t **out);

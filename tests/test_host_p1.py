@@ -65,3 +65,22 @@ def test_bad_arguments_raise(world):
         D.Algorithm("15d_fusion1", S, 8, 2)
     with pytest.raises(RuntimeError, match="perfect square"):
         D.Algorithm("25d_dense_replicate", S, 8, 3)
+
+
+def test_load_matrix_market_file(world, tmp_path):
+    """loadTuples(readFromFile = true): general and symmetric coordinate files, 1-based indices."""
+    gen = tmp_path / "g.mtx"
+    gen.write_text("%%MatrixMarket matrix coordinate real general\n% comment\n4 5 3\n1 1 2.5\n4 5 -1\n2 3 7\n")
+    S = D.SpmatLocal.load_file(str(gen))
+    assert S.info() == {"M": 4, "N": 5, "dist_nnz": 3, "local_tuples": 3}
+    r, c, v = S.tuples()
+    assert sorted(zip(r.tolist(), c.tolist(), v.tolist())) == [(0, 0, 2.5), (1, 2, 7.0), (3, 4, -1.0)]
+    sym = tmp_path / "s.mtx"
+    sym.write_text("%%MatrixMarket matrix coordinate pattern symmetric\n3 3 2\n2 1\n3 3\n")
+    S = D.SpmatLocal.load_file(str(sym))
+    r, c, v = S.tuples()
+    assert sorted(zip(r.tolist(), c.tolist(), v.tolist())) == [(0, 1, 1.0), (1, 0, 1.0), (2, 2, 1.0)]
+    alg = D.Algorithm("15d_fusion2", S, 4, 1)
+    assert alg.dims.M == 3 and alg.dims.s_values == 3
+    with pytest.raises(RuntimeError, match="cannot open"):
+        D.SpmatLocal.load_file(str(tmp_path / "missing.mtx"))
