@@ -1,4 +1,4 @@
-"""World size 2 and 4 on CPU (torch.distributed gloo through the External transport): the whole
+"""World size 2, 4 and 8 on CPU (torch.distributed gloo through the External transport): the whole
 host-side setup path of every algorithm -- tuple generation per rank, redistribute_nonzeros,
 block splitting, CSR construction, the 2.5D setup skew -- against the REFERENCE's own code
 (oracle/_ref: reference sources compiled with shims, MPI ranks as threads), rank by rank and
@@ -26,9 +26,18 @@ CASES_4 = [
     U.case("15d_fusion1", 2, 8, 7, 5, n=99),
     U.case("25d_dense_replicate", 1, 8, 7, 5, n=99),
 ]
+# the grid shapes of the 8-GPU runs (BASELINE.json configs 2-5): p=8 with c = 1, 2, 4, 8; 2.5D with s=2, c=2
+CASES_8 = [
+    U.case("15d_fusion2", 1, 8, 7, 5),
+    U.case("15d_fusion1", 4, 8, 7, 5),
+    U.case("15d_fusion2", 8, 8, 7, 5),
+    U.case("15d_sparse", 2, 8, 7, 5),
+    U.case("25d_dense_replicate", 2, 8, 7, 5),
+    U.case("25d_sparse_replicate", 2, 8, 7, 5),
+]
 
 
-@pytest.mark.parametrize("nproc,cases", [(2, CASES_2), (4, CASES_4)])
+@pytest.mark.parametrize("nproc,cases", [(2, CASES_2), (4, CASES_4), (8, CASES_8)])
 def test_setup_path_matches_reference_rank_by_rank(nproc, cases):
     cases = [dict(c, script=[]) for c in cases]
     got = U.run_cases(nproc, cases, "gloo")
