@@ -335,6 +335,9 @@ def run_native(args):
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
+        if args.e2e_pipeline:
+            alg.fusedSpMM_host(A, B, Sv, res, hA, hB, hO, "A")
+            return
         D.check(L.hnhd_dense_from_host(A.h, hA.data_ptr()), "from_host")
         D.check(L.hnhd_dense_from_host(B.h, hB.data_ptr()), "from_host")
         alg.fusedSpMM(A, B, Sv, res, "A")
@@ -351,7 +354,8 @@ def run_native(args):
     d2h = shapeA[0] * shapeA[1] * 8 * world
     e2e = {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "api": "per rank: DenseMatrix::copy_from_host(A), (B) from pinned memory; fusedSpMM; copy_to_host(A)"}
+           "api": ("per rank: Distributed_Sparse::fusedSpMM_host (pinned host A, B in; result out)" if args.e2e_pipeline else
+                   "per rank: DenseMatrix::copy_from_host(A), (B) from pinned memory; fusedSpMM; copy_to_host(A)")}
     del hA, hB, hO
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----
@@ -393,6 +397,9 @@ def main():
     ap.add_argument("--alg", default="15d_fusion2", choices=["15d_fusion1", "15d_fusion2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true")
+    ap.add_argument("--e2e-pipeline", action="store_true",
+                    help="e2e leg through fusedSpMM_host (upload / kernel / download pipelined on one rank); "
+                         "off until the path has been validated on a GPU")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.c <= 0:

@@ -280,6 +280,25 @@ int hnhd_alg_op(hnhd_alg_t *a, int op, hnhd_dense_t *A, hnhd_dense_t *B, hnhd_ve
     });
 }
 
+int hnhd_alg_fused_host(hnhd_alg_t *a, hnhd_dense_t *A, hnhd_dense_t *B, hnhd_vec_t *svals, hnhd_vec_t *result,
+                        const double *hostA, const double *hostB, double *hostOut, int mode, int64_t chunk_rows) {
+    return guarded([&] {
+        if (!a || !A || !B || !svals || !result || !hostA || !hostB || !hostOut || (mode != 0 && mode != 1))
+            throw hnh::Error(HNH_E_INVALID, "hnhd_alg_fused_host: bad argument");
+        Distributed_Sparse &d = *a->alg;
+        Sparse15D_Dense_Shift *ds = dynamic_cast<Sparse15D_Dense_Shift *>(&d);
+        const int64_t keep = ds ? ds->host_pipeline_chunk_rows : 0;
+        if (ds && chunk_rows != 0) ds->host_pipeline_chunk_rows = chunk_rows;
+        try {
+            d.fusedSpMM_host(hostA, hostB, hostOut, A->m, B->m, svals->v, result->v, mode == 0 ? Amat : Bmat);
+        } catch (...) {
+            if (ds) ds->host_pipeline_chunk_rows = keep;
+            throw;
+        }
+        if (ds) ds->host_pipeline_chunk_rows = keep;
+    });
+}
+
 int hnhd_timer_start(void) {
     return guarded([] {
         if (!g_t0) {

@@ -43,6 +43,16 @@ bool Runtime::has_device() {
 
 cudaStream_t Runtime::compute_stream() { init(); return compute_; }
 cudaStream_t Runtime::comm_stream() { init(); return comm_; }
+cudaStream_t Runtime::copy_in_stream() {
+    init();
+    if (!copy_in_) cuda_check(cudaStreamCreateWithFlags(&copy_in_, cudaStreamNonBlocking), "cudaStreamCreate");
+    return copy_in_;
+}
+cudaStream_t Runtime::copy_out_stream() {
+    init();
+    if (!copy_out_) cuda_check(cudaStreamCreateWithFlags(&copy_out_, cudaStreamNonBlocking), "cudaStreamCreate");
+    return copy_out_;
+}
 int Runtime::device() { init(); return dev_; }
 
 void Runtime::chain(cudaStream_t signaler, cudaStream_t waiter) {
@@ -57,6 +67,8 @@ void Runtime::sync_all() {
     if (!inited_) return;
     cuda_check(cudaStreamSynchronize(compute_), "sync compute");
     cuda_check(cudaStreamSynchronize(comm_), "sync comm");
+    if (copy_in_) cuda_check(cudaStreamSynchronize(copy_in_), "sync copy-in");
+    if (copy_out_) cuda_check(cudaStreamSynchronize(copy_out_), "sync copy-out");
 }
 
 void *Runtime::alloc(size_t bytes) {

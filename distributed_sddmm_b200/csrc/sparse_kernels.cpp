@@ -44,6 +44,27 @@ size_t StandardKernel::spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B,
     return 0;
 }
 
+void StandardKernel::fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block,
+                                      int64_t row0, int64_t nrows) {
+    CSRLocal *blk = S.csr_blocks[block];
+    if (nrows <= 0) return;
+    const int64_t r = X.cols();
+    if (blk == nullptr || blk->num_coords == 0) {
+        hnh::cuda_check(cudaMemsetAsync(Out.data() + row0 * r, 0, sizeof(double) * (size_t)(nrows * r),
+                                        Runtime::get().compute_stream()), "cudaMemsetAsync");
+        return;
+    }
+    if (blk->transpose) throw hnh::Error(HNH_E_MODE, "fused_local_rows needs a non-transposed block");
+    if (row0 < 0 || row0 + nrows > blk->rows) throw hnh::Error(HNH_E_INVALID, "fused_local_rows: row range");
+    CSRHandle *h = blk->getActive();
+    // rowStart entries are absolute offsets into col_idx / values, so a row range is the same call on shifted
+    // rowStart / X / Out pointers
+    abi_check(hnh_fused_f64(h->rowStart.data() + row0, h->col_idx.data(), h->values.data(), nrows, blk->num_coords,
+                            X.data() + row0 * r, B.data(), Out.data() + row0 * r, (int)r,
+                            flags | HNH_FLAG_BETA0_VALUES | HNH_FLAG_BETA0_OUT, Runtime::get().compute_stream()),
+              "hnh_fused_f64");
+}
+
 size_t StandardKernel::fused_local(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block,
                                    bool first_visit, bool out_is_zero) {
     CSRLocal *blk = S.csr_blocks[block];

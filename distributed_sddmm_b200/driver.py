@@ -242,6 +242,13 @@ class Algorithm:
     def fusedSpMM(self, A, B, S, R, mode="A"):
         self._op("fusedA" if mode == "A" else "fusedB", A, B, S, R)
 
+    def fusedSpMM_host(self, A, B, S, R, hostA, hostB, hostOut, mode="A", chunk_rows=0):
+        """fusedSpMM with host operands (torch CPU tensors or numpy arrays, float64, contiguous; pinned memory
+        makes the copies asynchronous).  chunk_rows: 0 default pipeline, < 0 no pipeline."""
+        ptr = lambda t: t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data  # noqa: E731
+        check(lib().hnhd_alg_fused_host(self.h, A.h, B.h, S.h, R.h, ptr(hostA), ptr(hostB), ptr(hostOut),
+                                        0 if mode == "A" else 1, chunk_rows), "hnhd_alg_fused_host")
+
     def initial_shift(self, A, B, mode):
         self._op("initial_shift", A, B, aux=KMODE[mode])
 

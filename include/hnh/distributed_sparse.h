@@ -115,6 +115,18 @@ public:
     virtual void fusedSpMM(DenseMatrix &localA, DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer,
                            MatMode mode);
 
+    // fusedSpMM on HOST operands, as the reference's callers hold them (Eigen matrices in host memory):
+    // hostA / hostB are this rank's local shards (row-major, like_A_matrix / like_B_matrix shapes), hostOut
+    // receives the SpMM result (the shape of the `mode` operand).  localA / localB are the device staging
+    // matrices.  Returns when hostOut is complete.  Subclasses may overlap the copies with the kernels.
+    virtual void fusedSpMM_host(const double *hostA, const double *hostB, double *hostOut, DenseMatrix &localA,
+                                DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer, MatMode mode) {
+        localA.copy_from_host(hostA);
+        localB.copy_from_host(hostB);
+        fusedSpMM(localA, localB, Svalues, sddmm_buffer, mode);
+        (mode == Amat ? localA : localB).copy_to_host(hostOut);
+    }
+
     virtual void algorithm(DenseMatrix &localA, DenseMatrix &localB, VectorXd &SValues, VectorXd *sddmm_result_ptr,
                            KernelMode mode, bool initial_replicate) = 0;
 

@@ -32,6 +32,9 @@ public:
     // Lazily binds to the current CUDA device and creates the streams.
     cudaStream_t compute_stream();
     cudaStream_t comm_stream();
+    // two more streams for host<->device copies that overlap kernels (fusedSpMM_host); created on first use
+    cudaStream_t copy_in_stream();
+    cudaStream_t copy_out_stream();
     int device();
     bool has_device();
     // make `waiter` wait for everything enqueued on `signaler` so far
@@ -55,7 +58,7 @@ private:
     void init();
     bool inited_ = false;
     int dev_ = -1;
-    cudaStream_t compute_ = nullptr, comm_ = nullptr;
+    cudaStream_t compute_ = nullptr, comm_ = nullptr, copy_in_ = nullptr, copy_out_ = nullptr;
     std::vector<cudaEvent_t> chain_events_;
     size_t chain_next_ = 0;
     size_t allocated_ = 0;

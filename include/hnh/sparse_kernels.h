@@ -69,4 +69,8 @@ public:
     size_t spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B, MatMode mode, int block) override;
     size_t fused_local(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block, bool first_visit,
                        bool out_is_zero) override;
+    // fused_local restricted to the CSR rows [row0, row0 + nrows) of the block, overwriting both the block's
+    // values and those rows of Out (Out may be X): the unit of the host-operand pipeline (fusedSpMM_host).
+    void fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block, int64_t row0,
+                          int64_t nrows);
 };

@@ -138,6 +138,14 @@ void hnhd_vec_destroy(hnhd_vec_t *v);
 int hnhd_alg_op(hnhd_alg_t *alg, int op, hnhd_dense_t *A, hnhd_dense_t *B, hnhd_vec_t *svals,
                 hnhd_vec_t *result, int aux);
 
+/* fusedSpMM on HOST operands (Distributed_Sparse::fusedSpMM_host, include/hnh/distributed_sparse.h): hostA / hostB
+ * are this rank's local shards in (preferably pinned) host memory, hostOut receives the SpMM result; A and B are
+ * the device staging matrices.  mode: 0 = Amat, 1 = Bmat.  chunk_rows > 0 sets the row chunk of the upload /
+ * kernel / download pipeline the 1.5D dense-shift algorithm runs on one rank, 0 keeps the default, < 0 turns the
+ * pipeline off (copy in, fusedSpMM, copy out).  Returns after hostOut is complete. */
+int hnhd_alg_fused_host(hnhd_alg_t *alg, hnhd_dense_t *A, hnhd_dense_t *B, hnhd_vec_t *svals, hnhd_vec_t *result,
+                        const double *hostA, const double *hostB, double *hostOut, int mode, int64_t chunk_rows);
+
 /* CUDA-event timing on the library's compute stream: start, ..., stop -> milliseconds. */
 int hnhd_timer_start(void);
 int hnhd_timer_stop(double *ms_out);

@@ -1,6 +1,8 @@
 """The distributed algorithm classes at p = 1 on the GPU, through the driver C ABI, against the
 global scipy/numpy reference (second oracle) and the dummyInitialize closed form.
 Multi-rank parity lives in tests/test_multirank_gpu.py."""
+import os
+
 import numpy as np
 import pytest
 
@@ -139,3 +141,37 @@ def test_als_cg_reduces_residual(world):
     for name in ALGS:
         before, after = D.Algorithm(name, S, 16, 1).als_residuals(1)
         assert np.isfinite([before, after]).all() and after < before, (name, before, after)
+
+
+# Paths written after this round's GPU budget was spent: compiled, never run on a device.  They are not on any
+# default code path; the first GPU session of the next round runs them with HNH_UNVALIDATED=1.
+unvalidated = pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1",
+                                 reason="not yet run on a GPU: set HNH_UNVALIDATED=1 (DESIGN.md section 7)")
+
+
+@unvalidated
+@pytest.mark.parametrize("name,chunk", [("15d_fusion2", 77), ("15d_fusion2", 256), ("15d_fusion2", 4096),
+                                        ("15d_fusion2", -1), ("15d_fusion1", 0), ("15d_sparse", 0)])
+def test_p1_fused_host_operands_match_device_path(world, problem, name, chunk):
+    """fusedSpMM_host (host operands in, result out; the 1.5D dense-shift algorithm pipelines upload / kernel /
+    download in row chunks on one rank) gives bit-identical results to copy in + fusedSpMM + copy out."""
+    P = problem
+    S = D.SpmatLocal.load_er(P["logM"], P["npr"], SEED)
+    alg = D.Algorithm(name, S, P["R"], 1)
+    A, B = alg.like_A_matrix(), alg.like_B_matrix()
+    for mode, like in (("A", alg.like_S_values), ("B", alg.like_ST_values)):
+        Sv, res = like(1.0), like(0.0)
+        A.from_host(P["A"])
+        B.from_host(P["B"])
+        alg.fusedSpMM(A, B, Sv, res, mode)
+        want = (A if mode == "A" else B).to_host()
+        want_values = res.to_host()
+        res2 = like(0.0)
+        hA, hB = np.ascontiguousarray(P["A"]), np.ascontiguousarray(P["B"])
+        out = np.full_like(hA, np.nan)
+        alg.fusedSpMM_host(A, B, Sv, res2, hA, hB, out, mode, chunk_rows=chunk)
+        assert np.array_equal(out, want)
+        if name != "15d_fusion2":  # local kernel fusion does not fill sddmm_buffer
+            assert np.array_equal(res2.to_host(), want_values)
+        # the staging matrices hold what the device path leaves there
+        assert np.array_equal((A if mode == "A" else B).to_host(), want)
