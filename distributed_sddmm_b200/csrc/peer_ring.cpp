@@ -3,6 +3,7 @@
 
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -155,8 +156,51 @@ void PeerRing::end_push(int k, cudaStream_t s) {
 void PeerRing::push(int k, const void *src, size_t bytes, cudaStream_t s) {
     if (owns_slots_ && bytes > bytes_) throw Error(HNH_E_INVALID, "PeerRing::push: shard larger than the slot");
     begin_push(k, s);
-    cuda_check(cudaMemcpyAsync(dst_[0][(size_t)k], src, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync(peer push)");
+    const int pieces = push_pieces();
+    if (pieces <= 1 || bytes < ((size_t)8 << 20)) {
+        cuda_check(cudaMemcpyAsync(dst_[0][(size_t)k], src, bytes, cudaMemcpyDeviceToDevice, s), "cudaMemcpyAsync(peer push)");
+    } else {
+        // Experiment (HNH_RING_PIECES, off by default): one copy engine may not fill an NVLink port; send the
+        // shard as `pieces` concurrent copies, piece 0 on `s`, the others on side streams forked from and
+        // joined back into `s` so that the arrival flag is still written after the whole shard.
+        static std::vector<cudaStream_t> side;
+        static std::vector<cudaEvent_t> done;
+        static cudaEvent_t fork = nullptr;
+        if (!fork) cuda_check(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "cudaEventCreate");
+        while ((int)side.size() < pieces - 1) {
+            cudaStream_t st;
+            cudaEvent_t ev;
+            cuda_check(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+            side.push_back(st);
+            done.push_back(ev);
+        }
+        const size_t piece = ((bytes / (size_t)pieces) + 255) & ~(size_t)255;
+        cuda_check(cudaEventRecord(fork, s), "cudaEventRecord");
+        for (int i = 0; i < pieces; i++) {
+            const size_t off = piece * (size_t)i;
+            if (off >= bytes) break;
+            const size_t n = std::min(piece, bytes - off);
+            cudaStream_t st = i == 0 ? s : side[(size_t)i - 1];
+            if (i > 0) cuda_check(cudaStreamWaitEvent(st, fork, 0), "cudaStreamWaitEvent");
+            cuda_check(cudaMemcpyAsync((char *)dst_[0][(size_t)k] + off, (const char *)src + off, n, cudaMemcpyDeviceToDevice, st),
+                       "cudaMemcpyAsync(peer push piece)");
+            if (i > 0) {
+                cuda_check(cudaEventRecord(done[(size_t)i - 1], st), "cudaEventRecord");
+                cuda_check(cudaStreamWaitEvent(s, done[(size_t)i - 1], 0), "cudaStreamWaitEvent");
+            }
+        }
+    }
     end_push(k, s);
+}
+
+int PeerRing::push_pieces() {
+    static const int n = [] {
+        const char *e = getenv("HNH_RING_PIECES");
+        const int v = e ? atoi(e) : 1;
+        return v < 1 ? 1 : (v > 8 ? 8 : v);
+    }();
+    return n;
 }
 
 void PeerRing::expect_arrival(int k) { expected_[k]++; }

@@ -63,6 +63,7 @@ public:
     // enqueue on `s`: tell the upstream rank that my slot k has been consumed
     void release(int k, cudaStream_t s);
 
+    static int push_pieces();   // HNH_RING_PIECES (default 1): concurrent copies one push() is split into
     static bool enabled();      // HNH_RING != "nccl"
     static bool all_shifts();   // also use copy-engine rings where the riding data is an output / a CSR block
 
