@@ -37,6 +37,9 @@ ABI = {
     "hnh_vec_quotient_f64": (C.c_int, [_P, _P, C.c_double, _P, C.c_double, _I64, _P]),
     "hnh_axpby_f64": (C.c_int, [_P, C.c_double, _P, C.c_double, _P, _I64, _P]),
     "hnh_squared_norm_f64": (C.c_int, [_P, _P, _I64, _P]),
+    "hnh_leaky_relu_f64": (C.c_int, [_P, _P, _I64, C.c_double, _P]),
+    "hnh_relu_cols_f64": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _P]),
+    "hnh_dgemm_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _I64, _P]),
     "hnh_block_create_host": (C.c_int, [_P, _P, _I64, _I64, _I64, C.c_int, C.POINTER(_P)]),
     "hnh_block_destroy": (None, [_P]),
     "hnh_block_run_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
@@ -160,6 +163,14 @@ ABI.update({
     "hnhd_vec_destroy": (None, [_P]),
     "hnhd_alg_op": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int]),
     "hnhd_alg_fused_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int64]),
+    "hnhd_gat_create": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.c_double, _PP]),
+    "hnhd_gat_weight_shape": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hnhd_gat_set_weight": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "hnhd_gat_buffer_shape": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hnhd_gat_set_input": (C.c_int, [_P, _P]),
+    "hnhd_gat_get_buffer": (C.c_int, [_P, C.c_int, _P]),
+    "hnhd_gat_forward": (C.c_int, [_P]),
+    "hnhd_gat_destroy": (None, [_P]),
     "hnhd_timer_start": (C.c_int, []),
     "hnhd_timer_stop": (C.c_int, [C.POINTER(C.c_double)]),
     "hnhd_als_residuals": (C.c_int, [_P, C.c_int, _P]),

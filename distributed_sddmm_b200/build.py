@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
         if verbose:
             sys.stderr.write(out.decode())
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", OUT, *objs, "-lnccl", "-lgomp"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "/usr/bin/g++", "-o", OUT, *objs, "-lnccl", "-lgomp", "-ldl"]
     subprocess.check_call(link)
     # stand-alone C++ driver with the reference's command line (tools/bench_er.cpp)
     exe = os.path.join(HERE, "bench_er")

@@ -13,6 +13,7 @@
 #include "hnh/25D_cannon_dense.hpp"
 #include "hnh/25D_cannon_sparse.hpp"
 #include "hnh/als_conjugate_gradients.h"
+#include "hnh/gat.hpp"
 #include "hnh_b200.h"
 
 Distributed_Sparse *hnh_make_algorithm(const string &name, SpmatLocal *spmat, int R, int c, KernelImplementation *k) {
@@ -32,8 +33,16 @@ json benchmark_algorithm_ex(SpmatLocal *spmat, string algorithm_name, string out
     StandardKernel local_ops;
     std::unique_ptr<Distributed_Sparse> d_ops(hnh_make_algorithm(algorithm_name, spmat, R, c, &local_ops));
     std::unique_ptr<Distributed_ALS> d_als;
-    if (app == "als") d_als.reset(new Distributed_ALS(d_ops.get(), true));
-    else if (app != "vanilla") throw hnh::Error(HNH_E_INVALID, "app must be \"vanilla\" or \"als\" (gat is out of scope)");
+    std::unique_ptr<GAT> gnn;
+    if (app == "gat") {
+        // the three layers of the reference's GAT benchmark: (input width, width per head, heads)
+        vector<GATLayer> layers{GATLayer(256, 256, 4), GATLayer(1024, 256, 4), GATLayer(1024, 256, 6)};
+        gnn.reset(new GAT(layers, d_ops.get()));
+    } else if (app == "als") {
+        d_als.reset(new Distributed_ALS(d_ops.get(), true));
+    } else if (app != "vanilla") {
+        throw hnh::Error(HNH_E_INVALID, "app must be \"vanilla\", \"als\" or \"gat\"");
+    }
 
     DenseMatrix A = d_ops->like_A_matrix(0.001);
     DenseMatrix B = d_ops->like_B_matrix(0.001);
@@ -50,6 +59,8 @@ json benchmark_algorithm_ex(SpmatLocal *spmat, string algorithm_name, string out
                 d_ops->sddmmA(A, B, Sv, sddmm_result);
                 d_ops->spmmA(A, B, Sv);
             }
+        } else if (app == "gat") {
+            gnn->forwardPass();
         } else {
             d_als->application_communication_time = 0.0;
             d_als->run_cg(1);

@@ -200,6 +200,20 @@ void DenseMatrix::copy_to_host(double *h) const {
 }
 vector<double> DenseMatrix::to_host() const { return buf_.to_host((size_t)size(), cs()); }
 
+void VectorXd::leakyRelu(double alpha) {
+    abi_check(hnh_leaky_relu_f64(data(), data(), n_, alpha, cs()), "leaky_relu");
+}
+DenseMatrix DenseMatrix::operator*(const DenseMatrix &o) const {
+    require(cols_ == o.rows(), "matrix product: inner dimensions differ");
+    DenseMatrix res(rows_, o.cols());
+    abi_check(hnh_dgemm_f64(res.data(), data(), o.data(), rows_, o.cols(), cols_, cs()), "dgemm");
+    return res;
+}
+void DenseMatrix::setMiddleColsRelu(int64_t start, const DenseMatrix &m) {
+    require(m.rows() == rows_ && start >= 0 && start + m.cols() <= cols_, "middleCols assignment: shape mismatch");
+    abi_check(hnh_relu_cols_f64(data(), cols_, start, m.data(), m.rows(), m.cols(), cs()), "relu_cols");
+}
+
 VectorXd batch_dot_product(const DenseMatrix &A, const DenseMatrix &B) {
     require(A.rows() == B.rows() && A.cols() == B.cols(), "batch_dot_product: shape mismatch");
     VectorXd r(A.rows());

@@ -11,6 +11,7 @@
 #include "hnh/als_conjugate_gradients.h"
 #include "hnh/benchmark_dist.hpp"
 #include "hnh/distributed_sparse.h"
+#include "hnh/gat.hpp"
 #include "hnh_b200.h"
 #include "launch.h"
 
@@ -28,6 +29,9 @@ struct hnhd_dense {
 };
 struct hnhd_vec {
     VectorXd v;
+};
+struct hnhd_gat {
+    std::unique_ptr<GAT> g;
 };
 
 namespace {
@@ -343,5 +347,71 @@ int hnhd_als_residuals(hnhd_alg_t *a, int steps, double *out2) {
         out2[1] = als.computeResidual();
     });
 }
+
+// ---- GAT ------------------------------------------------------------------------------------------
+int hnhd_gat_create(hnhd_alg_t *a, int n_layers, const int *layers3, double alpha, hnhd_gat_t **out) {
+    return guarded([&] {
+        if (!a || !layers3 || !out || n_layers <= 0) throw hnh::Error(HNH_E_INVALID, "hnhd_gat_create: bad argument");
+        vector<GATLayer> layers;
+        for (int i = 0; i < n_layers; i++) {
+            if (layers3[3 * i] <= 0 || layers3[3 * i + 1] <= 0 || layers3[3 * i + 2] <= 0)
+                throw hnh::Error(HNH_E_INVALID, "hnhd_gat_create: layer sizes must be positive");
+            layers.emplace_back(layers3[3 * i], layers3[3 * i + 1], layers3[3 * i + 2]);
+        }
+        std::unique_ptr<hnhd_gat> g(new hnhd_gat);
+        g->g.reset(new GAT(layers, a->alg.get()));
+        g->g->leaky_relu_alpha = alpha;
+        *out = g.release();
+    });
+}
+static DenseMatrix &gat_weight(hnhd_gat_t *g, int layer, int head) {
+    if (!g || layer < 0 || layer >= (int)g->g->layers.size()) throw hnh::Error(HNH_E_INVALID, "gat: no such layer");
+    GATLayer &l = g->g->layers[(size_t)layer];
+    if (head < 0 || head >= l.num_heads) throw hnh::Error(HNH_E_INVALID, "gat: no such head");
+    return l.wMats[(size_t)head];
+}
+static DenseMatrix &gat_buffer(hnhd_gat_t *g, int buffer) {
+    if (!g || buffer < 0 || buffer >= (int)g->g->buffers.size()) throw hnh::Error(HNH_E_INVALID, "gat: no such buffer");
+    return g->g->buffers[(size_t)buffer];
+}
+int hnhd_gat_weight_shape(hnhd_gat_t *g, int layer, int head, int64_t *rows, int64_t *cols) {
+    return guarded([&] {
+        DenseMatrix &w = gat_weight(g, layer, head);
+        if (rows) *rows = w.rows();
+        if (cols) *cols = w.cols();
+    });
+}
+int hnhd_gat_set_weight(hnhd_gat_t *g, int layer, int head, const double *host) {
+    return guarded([&] {
+        if (!host) throw hnh::Error(HNH_E_INVALID, "null host pointer");
+        gat_weight(g, layer, head).copy_from_host(host);
+    });
+}
+int hnhd_gat_buffer_shape(hnhd_gat_t *g, int buffer, int64_t *rows, int64_t *cols) {
+    return guarded([&] {
+        DenseMatrix &b = gat_buffer(g, buffer);
+        if (rows) *rows = b.rows();
+        if (cols) *cols = b.cols();
+    });
+}
+int hnhd_gat_set_input(hnhd_gat_t *g, const double *host) {
+    return guarded([&] {
+        if (!host) throw hnh::Error(HNH_E_INVALID, "null host pointer");
+        gat_buffer(g, 0).copy_from_host(host);
+    });
+}
+int hnhd_gat_get_buffer(hnhd_gat_t *g, int buffer, double *host) {
+    return guarded([&] {
+        if (!host) throw hnh::Error(HNH_E_INVALID, "null host pointer");
+        gat_buffer(g, buffer).copy_to_host(host);
+    });
+}
+int hnhd_gat_forward(hnhd_gat_t *g) {
+    return guarded([&] {
+        if (!g) throw hnh::Error(HNH_E_INVALID, "null gat");
+        g->g->forwardPass();
+    });
+}
+void hnhd_gat_destroy(hnhd_gat_t *g) { delete g; }
 
 }  // extern "C"

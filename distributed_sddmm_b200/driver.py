@@ -326,3 +326,49 @@ def benchmark_algorithm(S: SpmatLocal, name: str, R: int, c: int, fused=True, ap
     if n < 0:
         check(n, "hnhd_benchmark_algorithm")
     return json.loads(buf.value.decode())
+
+
+class GAT:
+    """Multi-head graph attention forward pass (include/hnh/gat.hpp).  layers: [(input_features,
+    features_per_head, num_heads), ...].  The algorithm object must outlive this one."""
+
+    def __init__(self, alg: Algorithm, layers, leaky_relu_alpha: float = 0.2):
+        self.alg = alg
+        self.layers = [tuple(int(x) for x in l) for l in layers]
+        flat = (C.c_int * (3 * len(self.layers)))(*[x for l in self.layers for x in l])
+        self.h = C.c_void_p()
+        check(lib().hnhd_gat_create(alg.h, len(self.layers), flat, float(leaky_relu_alpha), C.byref(self.h)), "gat_create")
+
+    def weight_shape(self, layer: int, head: int):
+        r, c = C.c_int64(), C.c_int64()
+        check(lib().hnhd_gat_weight_shape(self.h, layer, head, C.byref(r), C.byref(c)), "gat_weight_shape")
+        return r.value, c.value
+
+    def set_weight(self, layer: int, head: int, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert w.shape == self.weight_shape(layer, head), (w.shape, self.weight_shape(layer, head))
+        check(lib().hnhd_gat_set_weight(self.h, layer, head, w.ctypes.data), "gat_set_weight")
+
+    def buffer_shape(self, i: int):
+        r, c = C.c_int64(), C.c_int64()
+        check(lib().hnhd_gat_buffer_shape(self.h, i, C.byref(r), C.byref(c)), "gat_buffer_shape")
+        return r.value, c.value
+
+    def set_input(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == self.buffer_shape(0), (x.shape, self.buffer_shape(0))
+        check(lib().hnhd_gat_set_input(self.h, x.ctypes.data), "gat_set_input")
+
+    def buffer(self, i: int):
+        out = np.empty(self.buffer_shape(i), dtype=np.float64)
+        check(lib().hnhd_gat_get_buffer(self.h, i, out.ctypes.data), "gat_get_buffer")
+        return out
+
+    def forward(self):
+        check(lib().hnhd_gat_forward(self.h), "gat_forward")
+
+    def __del__(self):
+        try:
+            lib().hnhd_gat_destroy(self.h)
+        except Exception:
+            pass

@@ -70,6 +70,9 @@ public:
     double sum() const;
     // this[i] = (a[i] + ca) / (b[i] + cb): the alpha/coeff updates of cg_optimizer
     void setQuotient(const VectorXd &a, double ca, const VectorXd &b, double cb);
+    // this[i] = max(this[i], 0) + alpha * min(this[i], 0)
+    // (`v = v.array().max(0) + v.array().min(0) * alpha` of gat.hpp:98)
+    void leakyRelu(double alpha);
 
     // host interop (not in Eigen; the data lives in HBM)
     static VectorXd from_host(const double *h, int64_t n);
@@ -138,6 +141,11 @@ public:
     DenseMatrix operator-(const DenseMatrix &o) const;
     DenseMatrix cwiseProduct(const DenseMatrix &o) const;
     double squaredNorm() const;
+
+    // matrix product (gat.hpp:90 `buffers[i] * wMats[j]`): cuBLAS DGEMM on the compute stream
+    DenseMatrix operator*(const DenseMatrix &o) const;
+    // this.middleCols(start, m.cols()) = m.array().max(0)   (gat.hpp:104)
+    void setMiddleColsRelu(int64_t start, const DenseMatrix &m);
 
     // this = c + alpha * diag(s) * m  (row-scaled axpy; s empty == all ones). In place allowed.
     void setRowAxpy(const DenseMatrix &c, double alpha, const VectorXd *s, const DenseMatrix &m);

@@ -127,6 +127,18 @@ int hnh_axpby_f64(double *dst, double alpha, const double *x, double beta, const
 /* *out (device scalar) = sum x[i]^2 */
 int hnh_squared_norm_f64(double *out, const double *x, int64_t n, void *stream);
 
+/* ---- GAT forward pass helpers (reference gat.hpp:84-113; include/hnh/gat.hpp) --------------
+ * dst[i] = max(src[i], 0) + alpha * min(src[i], 0)   (gat.hpp:98; dst may alias src) */
+int hnh_leaky_relu_f64(double *dst, const double *src, int64_t n, double alpha, void *stream);
+/* dst[i, col0 + j] = max(src[i, j], 0) for a rows x cols src and a dst with ld_dst columns
+ * (buffers[i+1].middleCols(j * w, w) = A.array().max(0), gat.hpp:104) */
+int hnh_relu_cols_f64(double *dst, int64_t ld_dst, int64_t col0, const double *src, int64_t rows,
+                      int64_t cols, void *stream);
+/* C (m x n) = A (m x k) * B (k x n), all row-major and contiguous (buffers[i] * wMats[j],
+ * gat.hpp:90).  A plain library GEMM: cuBLAS, loaded on first use. */
+int hnh_dgemm_f64(double *C, const double *A, const double *B, int64_t m, int64_t n, int64_t k,
+                  void *stream);
+
 /* ---- host-side setup helpers (untimed; HOST pointers) --------------------------------------
  * hnh_er_generate_host replaces the CombBLAS Graph500 generator call of
  * SpmatLocal::loadTuples(false, logM, nnz_per_row) (SpmatLocal.hpp:499-516): rows

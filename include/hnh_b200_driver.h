@@ -163,6 +163,21 @@ int hnhd_benchmark_algorithm(hnhd_spmat_t *S, const char *algorithm_name, const 
  * out2 = {residual before, residual after} (world-reduced, identical on every rank).  Collective. */
 int hnhd_als_residuals(hnhd_alg_t *alg, int steps, double *out2);
 
+/* ---- GAT forward pass (include/hnh/gat.hpp; reference gat.hpp:26-113) -----------------------
+ * layers3: n_layers triples (input_features, features_per_head, num_heads).  The object keeps a
+ * pointer to `alg`, which must outlive it.  buffer 0 is the network input, buffer i + 1 the output
+ * of layer i; weights are input_width x head_width, row-major, as hnhd_gat_weight_shape reports. */
+typedef struct hnhd_gat hnhd_gat_t;
+int hnhd_gat_create(hnhd_alg_t *alg, int n_layers, const int *layers3, double leaky_relu_alpha,
+                    hnhd_gat_t **out);
+int hnhd_gat_weight_shape(hnhd_gat_t *g, int layer, int head, int64_t *rows, int64_t *cols);
+int hnhd_gat_set_weight(hnhd_gat_t *g, int layer, int head, const double *host);
+int hnhd_gat_buffer_shape(hnhd_gat_t *g, int buffer, int64_t *rows, int64_t *cols);
+int hnhd_gat_set_input(hnhd_gat_t *g, const double *host);          /* buffer 0 */
+int hnhd_gat_get_buffer(hnhd_gat_t *g, int buffer, double *host);   /* synchronises */
+int hnhd_gat_forward(hnhd_gat_t *g);                                /* forwardPass(); stream-ordered */
+void hnhd_gat_destroy(hnhd_gat_t *g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -188,3 +188,26 @@ def global_reference(rows, cols, vals, A, B):
     Sd = sp.csr_matrix((sddmm, S.indices, S.indptr), shape=(M, N))
     fused = Sd @ B
     return S, sddmm, spmmA, spmmB, fused
+
+
+def gat_forward_global(rows, cols, N, layers, weights, alpha, X0):
+    """GAT forward pass of the reference (gat.hpp:84-113) on GLOBAL matrices, for algorithms that do not split the
+    dense operands along R.  Per head: H = X W; e = <H_u, H_v> on every stored (u, v) (the pattern values are 1.0,
+    gat.hpp:87); e = max(e, 0) + alpha min(e, 0); Z = E H; out[:, head window] = max(Z, 0).  Pinned against the
+    reference's own code in tests/test_oracle_vs_ref.py."""
+    import scipy.sparse as sp
+
+    S = sp.csr_matrix((np.ones(len(rows)), (rows.astype(np.int64), cols.astype(np.int64))), shape=(N, N))
+    S.sort_indices()
+    ri = np.repeat(np.arange(N), np.diff(S.indptr))
+    X = np.asarray(X0, np.float64)
+    for (fin, fph, heads), ws in zip(layers, weights):
+        out = np.zeros((N, fph * heads))
+        for h in range(heads):
+            H = X @ np.asarray(ws[h], np.float64)
+            e = np.einsum("ij,ij->i", H[ri], H[S.indices])
+            e = np.maximum(e, 0.0) + np.minimum(e, 0.0) * alpha
+            Z = sp.csr_matrix((e, S.indices, S.indptr), shape=(N, N)) @ H
+            out[:, h * fph:(h + 1) * fph] = np.maximum(Z, 0.0)
+        X = out
+    return X

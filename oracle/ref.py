@@ -164,3 +164,55 @@ def time_fused(alg, p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per
     nnz = lib().ref_time_fused(alg.encode(), p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per_rank,
                                secs.ctypes.data)
     return int(nnz), secs
+
+
+def gat(alg, p, c, N, rows, cols, vals, layers, weights, alpha, X0, threads_per_rank: int = 1):
+    """The REFERENCE's GAT forward pass (gat.hpp) on p thread-ranks.  layers: [(in, per_head, heads)];
+    weights[i][h]: in x per_head; X0: N x layers[0][0].  Returns (global output N x out_width, per-rank list of
+    (local buffer, aSubmatrices))."""
+    L = lib()
+    P = C.c_void_p
+    L.ref_gat.restype = P
+    L.ref_gat.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, C.c_int, P, P,
+                          C.c_double, P, C.c_int]
+    L.ref_gat_error.restype = C.c_char_p
+    L.ref_gat_error.argtypes = [P]
+    L.ref_gat_shape_len.argtypes = [P, C.c_int]
+    L.ref_gat_shape.restype = P
+    L.ref_gat_shape.argtypes = [P, C.c_int]
+    L.ref_gat_out.restype = P
+    L.ref_gat_out.argtypes = [P, C.c_int]
+    L.ref_gat_free.argtypes = [P]
+    rows = np.ascontiguousarray(rows, np.uint64)
+    cols = np.ascontiguousarray(cols, np.uint64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    l3 = np.ascontiguousarray(np.array(layers, dtype=np.int32).reshape(-1))
+    w = np.ascontiguousarray(np.concatenate([np.asarray(weights[i][h], np.float64).reshape(-1)
+                                             for i in range(len(layers)) for h in range(layers[i][2])]))
+    X0 = np.ascontiguousarray(X0, np.float64)
+    h = L.ref_gat(alg.encode(), p, c, N, N, len(rows), rows.ctypes.data, cols.ctypes.data, vals.ctypes.data, len(layers),
+                  l3.ctypes.data, w.ctypes.data, float(alpha), X0.ctypes.data, threads_per_rank)
+    try:
+        err = L.ref_gat_error(h).decode()
+        if err:
+            raise RuntimeError(err)
+        outw = layers[-1][1] * layers[-1][2]
+        G = np.zeros((N, outw))
+        per_rank = []
+        for rank in range(p):
+            n = L.ref_gat_shape_len(h, rank)
+            sh = _arr(L.ref_gat_shape(h, rank), n, np.int32)
+            nr, nc = int(sh[0]), int(sh[1])
+            subs = sh[2:].reshape(-1, 4)
+            loc = _arr(L.ref_gat_out(h, rank), nr * nc, np.float64).reshape(nr, nc)
+            per_rank.append((loc, subs))
+            at, flat = 0, loc.reshape(-1)
+            for top, left, snr, snc in subs:
+                blk = flat[at:at + snr * snc].reshape(snr, snc)
+                at += snr * snc
+                hi = min(top + snr, N)
+                if hi > top:
+                    G[top:hi, left:left + snc] = blk[:hi - top]
+        return G, per_rank
+    finally:
+        L.ref_gat_free(h)

@@ -23,6 +23,7 @@
 #include "benchmark_dist.hpp"
 #include "common.h"
 #include "distributed_sparse.h"
+#include "gat.hpp"
 #include "sparse_kernels.h"
 
 uint64_t hnh_shim_er_seed = 0xC0FFEEull;
@@ -306,5 +307,86 @@ int64_t ref_time_fused(const char *alg, int p, int c, int R, int logM, int nnz_p
     hmpi_run(p, threads_per_rank, time_main, &a);
     return a.nnz;
 }
+
+
+// The reference's GAT forward pass (gat.hpp:49-113) on caller inputs: global features X0 (N x layers[0].in),
+// one global weight matrix per (layer, head) -- every rank holds the same copy -- and an explicit
+// leaky_relu_alpha (the reference never assigns it).  Only meaningful where the dense operands are not split
+// along R (the 1.5D dense-shift algorithms, or any algorithm on one rank): the harness refuses other shapes.
+// Output per rank: the last layer's buffer and the A-submatrix descriptors at R = its width.
+struct GatArgs {
+    Job *job;
+    int n_layers;
+    const int *layers3;
+    const double *weights;  // concatenated (layer, head) matrices, each in x head_width row-major
+    double alpha;
+    const double *X0;
+    std::vector<std::vector<double>> out;
+    std::vector<std::vector<int>> shape;  // rows, cols, then 4 ints per A submatrix
+};
+static void gat_main(int rank, void *arg) {
+    GatArgs &G = *(GatArgs *)arg;
+    Job &J = *G.job;
+    initialize_mpi_datatypes();
+    SpmatLocal S;
+    const int64_t per = (J.nnz + J.p - 1) / J.p, lo = std::min<int64_t>(per * rank, J.nnz), hi = std::min<int64_t>(lo + per, J.nnz);
+    S.coords.resize((size_t)(hi - lo));
+    for (int64_t t = lo; t < hi; t++) S.coords[(size_t)(t - lo)] = spcoord_t{J.rows[t], J.cols[t], J.vals[t]};
+    S.M = (uint64_t)J.M; S.N = (uint64_t)J.N; S.dist_nnz = (uint64_t)J.nnz; S.initialized = true;
+    StandardKernel kernel;
+    Distributed_Sparse *d = make_alg(J.alg, &S, G.layers3[0], J.c, &kernel);
+    if (!d) { std::lock_guard<std::mutex> lk(J.mu); J.error = "unknown algorithm " + J.alg; return; }
+    std::vector<GATLayer> layers;
+    for (int i = 0; i < G.n_layers; i++) layers.emplace_back(G.layers3[3 * i], G.layers3[3 * i + 1], G.layers3[3 * i + 2]);
+    GAT gnn(layers, d);
+    gnn.leaky_relu_alpha = G.alpha;
+    const double *w = G.weights;
+    bool ok = true;
+    for (int i = 0; i < G.n_layers; i++)
+        for (int h = 0; h < G.layers3[3 * i + 2]; h++) {
+            DenseMatrix &W = gnn.layers[(size_t)i].wMats[(size_t)h];
+            const long in = G.layers3[3 * i], fph = G.layers3[3 * i + 1];
+            if (W.rows() != in || W.cols() != fph) ok = false;
+            else std::memcpy(W.data(), w, sizeof(double) * (size_t)(in * fph));
+            w += in * fph;
+        }
+    if (!ok) {
+        std::lock_guard<std::mutex> lk(J.mu);
+        J.error = "GAT harness: this algorithm splits the dense operands along R on this grid";
+    } else {
+        d->setRValue(G.layers3[0]);
+        gather_local(gnn.buffers[0], d->bSubmatrices, G.X0, J.N, G.layers3[0]);
+    }
+    MPI_Barrier(MPI_COMM_WORLD);
+    if (!J.error.empty()) { delete d; return; }
+    gnn.forwardPass();
+    const int outw = G.layers3[3 * (G.n_layers - 1) + 1] * G.layers3[3 * (G.n_layers - 1) + 2];
+    d->setRValue(outw);
+    DenseMatrix &last = gnn.buffers.back();
+    G.out[(size_t)rank] = flatten(last);
+    std::vector<int> &sh = G.shape[(size_t)rank];
+    sh.push_back((int)last.rows()); sh.push_back((int)last.cols());
+    for (auto &s : d->aSubmatrices) { sh.push_back(s.topRow); sh.push_back(s.leftCol); sh.push_back(s.rowCount); sh.push_back(s.colCount); }
+    delete d;
+}
+struct ref_gat_result { Job job; GatArgs args; };
+ref_gat_result *ref_gat(const char *alg, int p, int c, int64_t M, int64_t N, int64_t nnz, const uint64_t *rows, const uint64_t *cols,
+                        const double *vals, int n_layers, const int *layers3, const double *weights, double alpha,
+                        const double *X0, int threads_per_rank) {
+    ref_gat_result *r = new ref_gat_result();
+    Job &J = r->job;
+    J.alg = alg; J.p = p; J.c = c; J.R = layers3[0]; J.M = M; J.N = N; J.nnz = nnz; J.rows = rows; J.cols = cols; J.vals = vals;
+    J.A = nullptr; J.B = nullptr;
+    GatArgs &G = r->args;
+    G.job = &J; G.n_layers = n_layers; G.layers3 = layers3; G.weights = weights; G.alpha = alpha; G.X0 = X0;
+    G.out.resize((size_t)p); G.shape.resize((size_t)p);
+    hmpi_run(p, threads_per_rank, gat_main, &G);
+    return r;
+}
+const char *ref_gat_error(ref_gat_result *r) { return r->job.error.c_str(); }
+int ref_gat_shape_len(ref_gat_result *r, int rank) { return (int)r->args.shape[(size_t)rank].size(); }
+const int *ref_gat_shape(ref_gat_result *r, int rank) { return r->args.shape[(size_t)rank].data(); }
+const double *ref_gat_out(ref_gat_result *r, int rank) { return r->args.out[(size_t)rank].data(); }
+void ref_gat_free(ref_gat_result *r) { delete r; }
 
 }  // extern "C"

@@ -26,6 +26,15 @@ def global_inputs(N, R, seed):
     return rng.uniform(-1, 1, (N, R)), rng.uniform(-1, 1, (N, R))
 
 
+def gat_inputs(N, layers, seed):
+    """Deterministic GAT test inputs: (layers as tuples, X0 (N x in), weights[layer][head] (in x per_head))."""
+    layers = [tuple(int(x) for x in l) for l in layers]
+    rng = np.random.default_rng(seed + 77)
+    X0 = rng.uniform(-1, 1, (N, layers[0][0]))
+    weights = [[rng.uniform(-1, 1, (fin, fph)) for _ in range(heads)] for fin, fph, heads in layers]
+    return layers, X0, weights
+
+
 def gather_local(G, subs, shape):
     out = np.zeros(shape)
     flat = out.reshape(-1)
@@ -138,6 +147,19 @@ def main():
             out["perf"] = json.dumps(alg.perf())
             if case.get("als"):
                 out["als"] = np.array(alg.als_residuals(1))
+        if have_gpu and case.get("gat"):
+            # GAT forward pass on this algorithm object (dense-shift layouts: one row block per rank, full width)
+            g = case["gat"]
+            layers, X0, weights = gat_inputs(N, g["layers"], seed)
+            net = D.GAT(alg, layers, g["alpha"])
+            for i, (fin, fph, heads) in enumerate(layers):
+                for h in range(heads):
+                    net.set_weight(i, h, weights[i][h])
+            top, _, nr, _ = alg.submatrices("B")[0]
+            net.set_input(gather_local(X0, [(top, 0, nr, layers[0][0])], net.buffer_shape(0)))
+            net.forward()
+            out["gat_out"] = net.buffer(len(layers))
+            del net
         out["info"] = json.dumps(alg.info())
         np.savez(os.path.join(outdir, f"{name}_rank{rank}.npz"), **out)
         del alg, S

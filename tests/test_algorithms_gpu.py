@@ -175,3 +175,58 @@ def test_p1_fused_host_operands_match_device_path(world, problem, name, chunk):
             assert np.array_equal(res2.to_host(), want_values)
         # the staging matrices hold what the device path leaves there
         assert np.array_equal((A if mode == "A" else B).to_host(), want)
+
+
+@unvalidated
+def test_gat_device_helpers(world):
+    """hnh_leaky_relu_f64 / hnh_relu_cols_f64 / hnh_dgemm_f64 against numpy."""
+    import torch
+    from distributed_sddmm_b200 import lib
+    L = lib()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-1, 1, 10007)
+    dx = torch.from_numpy(x).to(dev)
+    D.check(L.hnh_leaky_relu_f64(dx.data_ptr(), dx.data_ptr(), x.size, 0.25, st))
+    assert np.array_equal(dx.cpu().numpy(), np.maximum(x, 0) + np.minimum(x, 0) * 0.25)
+    src = rng.uniform(-1, 1, (33, 5))
+    dst = rng.uniform(-1, 1, (33, 17))
+    dsrc, ddst = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+    D.check(L.hnh_relu_cols_f64(ddst.data_ptr(), 17, 10, dsrc.data_ptr(), 33, 5, st))
+    want = dst.copy()
+    want[:, 10:15] = np.maximum(src, 0)
+    assert np.array_equal(ddst.cpu().numpy(), want)
+    assert L.hnh_relu_cols_f64(ddst.data_ptr(), 17, 13, dsrc.data_ptr(), 33, 5, st) == -1  # window past the row end
+    A, B = rng.uniform(-1, 1, (70, 19)), rng.uniform(-1, 1, (19, 11))
+    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+    dC = torch.empty((70, 11), dtype=torch.float64, device=dev)
+    D.check(L.hnh_dgemm_f64(dC.data_ptr(), dA.data_ptr(), dB.data_ptr(), 70, 11, 19, st))
+    torch.cuda.synchronize()
+    assert rel_err(dC.cpu().numpy(), A @ B) < 1e-13
+
+
+@unvalidated
+@pytest.mark.parametrize("name", ALGS)
+def test_p1_gat_forward_matches_global_model(world, name):
+    """GAT forward pass on one rank (every algorithm has full-width operands there) against the numpy model
+    that tests/test_oracle_vs_ref.py pins to the reference's gat.hpp."""
+    from tests.mp_worker import gat_inputs
+    logM, npr = 8, 6
+    N = 1 << logM
+    rows, cols, _ = orc.er_tuples(logM, npr, SEED)
+    layers, X0, weights = gat_inputs(N, [[12, 8, 2], [16, 4, 3]], SEED)
+    S = D.SpmatLocal.load_er(logM, npr, SEED)
+    alg = D.Algorithm(name, S, layers[0][0], 1)
+    net = D.GAT(alg, layers, 0.2)
+    assert net.buffer_shape(0) == (N, 12) and net.buffer_shape(2) == (N, 12)
+    for i, (fin, fph, heads) in enumerate(layers):
+        for h in range(heads):
+            assert net.weight_shape(i, h) == (fin, fph)
+            net.set_weight(i, h, weights[i][h])
+    net.set_input(X0)
+    net.forward()
+    want = orc.gat_forward_global(rows, cols, N, layers, weights, 0.2, X0)
+    assert (want != 0).mean() > 0.2
+    assert rel_err(net.buffer(2), want) < RTOL
+    assert rel_err(net.buffer(1), orc.gat_forward_global(rows, cols, N, layers[:1], weights[:1], 0.2, X0)) < RTOL

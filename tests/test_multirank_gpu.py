@@ -6,6 +6,8 @@ How the ranks are mapped: with at least `nproc` GPUs each rank gets its own GPU 
 shifts / collectives are NCCL; on a one-GPU box the ranks are processes sharing cuda:0 and the
 External transport (gloo, device buffers staged through pinned memory) carries the messages, so
 the algorithm code under test is identical."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -62,3 +64,38 @@ def test_all_operations_match_reference(nproc):
             assert all(np.array_equal(res[0], x) for x in res), (c["name"], res)
             assert np.isfinite(res[0]).all() and res[0][1] < res[0][0], (c["name"], res[0])
     print(f"nproc={nproc}: {checked} cases, worst relative error {worst:.2e}")
+
+
+GAT = dict(layers=[[6, 4, 2], [8, 3, 3]], alpha=0.2)
+GAT_CASES = {
+    2: [dict(U.case("15d_fusion1", 1, 6, 7, 5, script=[], name="gat_fusion1_c1"), gat=GAT),
+        dict(U.case("15d_fusion2", 1, 6, 7, 5, script=[], name="gat_fusion2_c1"), gat=GAT),
+        dict(U.case("15d_fusion2", 2, 6, 7, 5, script=[], name="gat_fusion2_c2"), gat=GAT)],
+    4: [dict(U.case("15d_fusion1", 2, 6, 7, 5, script=[], name="gat_fusion1_c2"), gat=GAT),
+        dict(U.case("15d_fusion2", 1, 6, 7, 5, script=[], name="gat_fusion2_c1"), gat=GAT)],
+}
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_gat_forward_matches_reference(nproc):
+    """GAT forward pass (include/hnh/gat.hpp) rank by rank against the reference's gat.hpp run by oracle/_ref --
+    including the fusion-2, c > 1 case where the reference's SpMM pass accumulates onto the gathered
+    projection (15D_dense_shift.hpp:306-314 with initial_replicate = false)."""
+    from oracle import hnh_oracle as orc
+    from oracle import ref
+    from tests.mp_worker import gat_inputs
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built")
+    cases = GAT_CASES[nproc]
+    got = U.run_cases(nproc, cases, transport_for(nproc), timeout=900)
+    for c in cases:
+        N = 1 << c["logM"]
+        rows, cols, _ = orc.er_tuples(c["logM"], c["npr"], c["seed"])
+        layers, X0, weights = gat_inputs(N, c["gat"]["layers"], c["seed"])
+        _, per_rank = ref.gat(c["alg"], nproc, c["c"], N, rows, cols, np.ones(len(rows)), layers, weights, c["gat"]["alpha"], X0)
+        for r, (want, _) in enumerate(per_rank):
+            have = got[c["name"]][r]["gat_out"]
+            assert have.shape == want.shape, (c["name"], r, have.shape, want.shape)
+            err = np.abs(have - want).max() / max(np.abs(want).max(), 1e-300)
+            assert err < 1e-11, (c["name"], r, err)

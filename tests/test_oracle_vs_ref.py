@@ -88,3 +88,26 @@ def test_reference_benchmark_entry_point_runs(tmp_path):
     rec = json.loads(out.read_text().strip().rstrip(","))
     assert rec["alg_name"] == "15d_fusion1" and rec["num_trials"] == 5 and rec["alg_info"]["p"] == 2
     assert rec["alg_info"]["nnz"] == len(orc.er_tuples(10, 8, 0xC0FFEE)[0])
+
+
+@pytest.mark.parametrize("alg,p,c", [("15d_fusion1", 1, 1), ("15d_fusion2", 1, 1), ("15d_sparse", 1, 1),
+                                     ("25d_dense_replicate", 1, 1), ("25d_sparse_replicate", 1, 1),
+                                     ("15d_fusion1", 2, 1), ("15d_fusion1", 4, 2), ("15d_fusion1", 8, 8),
+                                     ("15d_fusion2", 2, 1), ("15d_fusion2", 4, 1), ("15d_fusion2", 8, 1)])
+def test_gat_global_model_matches_the_reference_gat(alg, p, c):
+    """orc.gat_forward_global against the reference's gat.hpp (forward pass, two layers, several heads, random
+    weights, explicit alpha) wherever the dense operands keep their full width: one rank, or the 1.5D dense-shift
+    algorithms.  (Fusion 2 with c > 1 is left out: there the reference's SpMM pass, called with initial_replicate =
+    false, accumulates onto the gathered projection left by the SDDMM pass -- 15D_dense_shift.hpp:306-314 -- so its
+    output is not the GAT formula; the GPU test compares that case against the reference run itself.)"""
+    logM, npr = 7, 5
+    N = 1 << logM
+    rows, cols, _ = orc.er_tuples(logM, npr, 0xC0FFEE + 1)
+    rng = np.random.default_rng(3)
+    layers = [(6, 4, 2), (8, 3, 3)]
+    weights = [[rng.uniform(-1, 1, (fin, fph)) for _ in range(h)] for fin, fph, h in layers]
+    X0 = rng.uniform(-1, 1, (N, layers[0][0]))
+    want = orc.gat_forward_global(rows, cols, N, layers, weights, 0.2, X0)
+    assert (want != 0).mean() > 0.3 and (want == 0).mean() > 0.1  # both ReLU branches are exercised
+    got, _ = ref.gat(alg, p, c, N, rows, cols, np.ones(len(rows)), layers, weights, 0.2, X0)
+    assert np.abs(got - want).max() / np.abs(want).max() < 1e-13
