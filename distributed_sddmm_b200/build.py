@@ -77,8 +77,22 @@ def build_reference_driver() -> str | None:
     src = "/root/reference/bench_erdos_renyi.cpp"
     if not os.path.exists(src):
         return None
-    exe = os.path.join(HERE, "bench_er_reference_main")
-    obj = os.path.join(HERE, "build", "bench_er_reference_main.o")
+    exe = _compile_reference_main(src, "bench_er_reference_main")
+    # the reference's two other drivers (MatrixMarket file input; sweep over R), same recipe
+    for other, name in (("bench_file.cpp", "bench_file_reference_main"), ("bench_heatmap.cpp", "bench_heatmap_reference_main")):
+        path = os.path.join("/root/reference", other)
+        if os.path.exists(path):
+            try:
+                _compile_reference_main(path, name)
+            except subprocess.CalledProcessError as e:  # the headline driver above is the required one
+                sys.stderr.write(f"build: {other} did not compile against include/hnh/compat ({e})\n")
+    return exe
+
+
+def _compile_reference_main(src: str, name: str) -> str:
+    exe = os.path.join(HERE, name)
+    obj = os.path.join(HERE, "build", name + ".o")
+    os.makedirs(os.path.dirname(obj), exist_ok=True)
     with open(src, "rb") as f:
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-x", "c++", "-c", "-o", obj,
                                "-I" + os.path.join(ROOT, "include", "hnh", "compat"), "-I" + os.path.join(ROOT, "include"),

@@ -16,6 +16,8 @@ def test_reference_driver_compiles_unchanged():
     from distributed_sddmm_b200 import build
     exe = build.build_reference_driver()
     assert exe and os.path.exists(exe)
+    for other in ("bench_file_reference_main", "bench_heatmap_reference_main"):  # bench_file.cpp, bench_heatmap.cpp
+        assert os.path.exists(os.path.join(PKG, other)), other
     import torch
     if not torch.cuda.is_available():
         # no CPU fallback: the program must refuse to run without a GPU
@@ -38,3 +40,27 @@ def test_cpp_drivers_run_on_gpu(exe, tmp_path):
     for r in records:
         assert r["fused"] is True and r["num_trials"] == 5 and r["overall_throughput"] > 0
         assert r["alg_info"]["m"] == 4096 and r["alg_info"]["r"] == 32 and r["alg_info"]["p"] == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+def test_reference_file_driver_runs_on_gpu(tmp_path):
+    """The reference's bench_file.cpp (MatrixMarket input, unfused SDDMM + SpMM on the 1.5D sparse-shift algorithm),
+    compiled unchanged."""
+    path = os.path.join(PKG, "bench_file_reference_main")
+    if not os.path.exists(path):
+        pytest.skip("bench_file_reference_main not built")
+    import numpy as np
+    from oracle import hnh_oracle as orc
+    rows, cols, _ = orc.er_tuples(10, 6, 5)
+    mtx = tmp_path / "er.mtx"
+    with open(mtx, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write(f"1024 1024 {len(rows)}\n")
+        np.savetxt(f, np.column_stack([rows + 1, cols + 1, np.ones(len(rows))]), fmt="%d %d %g")
+    out = tmp_path / "records.json"
+    p = subprocess.run([path, str(mtx), "15d", "32", "1", str(out), "vanilla"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    records = json.loads("[" + out.read_text().strip().rstrip(",") + "]")
+    assert [r["alg_name"] for r in records] == ["15d_sparse"] and records[0]["fused"] is False
+    assert records[0]["alg_info"]["nnz"] == len(rows) and records[0]["overall_throughput"] > 0
