@@ -154,6 +154,17 @@ int hnh_coo_to_csr_host(int64_t rows, int64_t cols, int64_t nnz, const uint64_t 
                         const uint64_t *c, const double *v, int transpose, int64_t *rowStart,
                         int64_t *col_idx, int64_t *row_idx, double *values);
 
+/* Device versions of the two helpers above (DEVICE pointers; untimed setup; they synchronise `stream`
+ * before returning).  Output is bit-identical with the host versions: the generator is a pure function
+ * of (seed, row, k), the CSR order is a stable sort by stored row.  nnz_per_row <= 128; one block holds
+ * fewer than 2^31 entries. */
+int64_t hnh_er_generate_device(int logM, int nnz_per_row, uint64_t seed, int64_t row_lo,
+                               int64_t row_hi, uint64_t *rows_out, uint64_t *cols_out,
+                               double *vals_out, int64_t capacity, void *stream);
+int hnh_coo_to_csr_device(int64_t rows, int64_t cols, int64_t nnz, const uint64_t *r,
+                          const uint64_t *c, const double *v, int transpose, int64_t *rowStart,
+                          int64_t *col_idx, int64_t *row_idx, double *values, void *stream);
+
 /* ---- host-buffer entry points (pinned or pageable HOST pointers) -------------------------
  * One call = H2D of the dense operands and values, the kernel(s), D2H of the results, all
  * inside the call; the block's CSR structure is taken from a resident handle made once with

@@ -5,10 +5,13 @@ within 1e-5 relative (BASELINE.json north_star) -- we assert the much tighter 1e
 arithmetic actually achieves, and bit-exactness for SpMM where the summation order matches
 the oracle's.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
 
+from distributed_sddmm_b200 import lib
 from oracle import hnh_oracle as orc
 from tests import gpu_util as gu
 
@@ -303,3 +306,68 @@ def test_tma_per_warp_variant_matches_direct(hnh, R):
         v, o = gu.run_fused(csr, v0, A, B, O0, flags=WARP | extra)
         vd, od = gu.run_fused(csr, v0, A, B, O0, flags=DIRECT | extra)
         assert np.array_equal(v, vd) and np.array_equal(o, od)
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("logM,npr,lo,hi", [(10, 8, 0, 1024), (12, 32, 100, 3000), (6, 64, 0, 64), (14, 1, 5, 6)])
+def test_device_er_generator_is_bit_identical_with_host(logM, npr, lo, hi):
+    """hnh_er_generate_device against hnh_er_generate_host (rows, columns, values, count); npr = 64 on 64 columns
+    forces many duplicate draws."""
+    import torch
+    L = lib()
+    cap = (hi - lo) * npr
+    hr, hc, hv = np.empty(cap, np.uint64), np.empty(cap, np.uint64), np.empty(cap, np.float64)
+    n = L.hnh_er_generate_host(logM, npr, 0xC0FFEE + 2, lo, hi, hr.ctypes.data, hc.ctypes.data, hv.ctypes.data, cap)
+    assert n > 0
+    dev = torch.device("cuda:0")
+    dr = torch.zeros(cap, dtype=torch.int64, device=dev)
+    dc = torch.zeros(cap, dtype=torch.int64, device=dev)
+    dv = torch.zeros(cap, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    m = L.hnh_er_generate_device(logM, npr, 0xC0FFEE + 2, lo, hi, dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), cap, st)
+    assert m == n
+    assert np.array_equal(dr.cpu().numpy()[:n].view(np.uint64), hr[:n])
+    assert np.array_equal(dc.cpu().numpy()[:n].view(np.uint64), hc[:n])
+    assert np.array_equal(dv.cpu().numpy()[:n], hv[:n])
+    assert L.hnh_er_generate_device(logM, npr, 1, lo, hi, dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), 1, st) == -1 or n <= 1
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("transpose", [0, 1])
+@pytest.mark.parametrize("rows,cols,logM,npr", [(1024, 1024, 10, 8), (300, 4096, 12, 16), (1, 64, 6, 64), (512, 512, 9, 1)])
+def test_device_coo_to_csr_is_bit_identical_with_host(rows, cols, logM, npr, transpose):
+    """hnh_coo_to_csr_device against hnh_coo_to_csr_host on tuples in (col, row) order -- the order redistributed
+    tuples arrive in (SpmatLocal.hpp:458) -- with and without transposition; duplicates keep their input order."""
+    import torch
+    L = lib()
+    from oracle import hnh_oracle as orc
+    r, c, _ = orc.er_tuples(logM, npr, 0xC0FFEE + 4, 0, rows)
+    order = np.lexsort((r, c))
+    r, c = np.ascontiguousarray(r[order]), np.ascontiguousarray(c[order])
+    # duplicates with distinct values: stability is observable
+    r, c = np.concatenate([r, r[:7]]), np.concatenate([c, c[:7]])
+    v = np.arange(len(r), dtype=np.float64) + 0.5
+    nnz = len(r)
+    out_rows = cols if transpose else rows
+    h_rs, h_ci, h_ri, h_v = np.empty(out_rows + 1, np.int64), np.empty(nnz, np.int64), np.empty(nnz, np.int64), np.empty(nnz)
+    assert L.hnh_coo_to_csr_host(rows, cols, nnz, r.ctypes.data, c.ctypes.data, v.ctypes.data, transpose, h_rs.ctypes.data,
+                                 h_ci.ctypes.data, h_ri.ctypes.data, h_v.ctypes.data) == 0
+    dev = torch.device("cuda:0")
+    T = lambda a: torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).to(dev)  # noqa: E731
+    dr, dc, dv = T(r), T(c), T(v)
+    d_rs = torch.full((out_rows + 1,), -1, dtype=torch.int64, device=dev)
+    d_ci, d_ri = torch.full((nnz,), -1, dtype=torch.int64, device=dev), torch.full((nnz,), -1, dtype=torch.int64, device=dev)
+    d_v = torch.zeros(nnz, dtype=torch.float64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.hnh_coo_to_csr_device(rows, cols, nnz, dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), transpose, d_rs.data_ptr(),
+                                   d_ci.data_ptr(), d_ri.data_ptr(), d_v.data_ptr(), st) == 0
+    assert np.array_equal(d_rs.cpu().numpy(), h_rs)
+    assert np.array_equal(d_ci.cpu().numpy(), h_ci)
+    assert np.array_equal(d_ri.cpu().numpy(), h_ri)
+    assert np.array_equal(d_v.cpu().numpy(), h_v)
+    # a coordinate outside the block is refused
+    bad = T(np.array([rows], np.uint64)) if not transpose else T(np.array([cols + 5], np.uint64))
+    one = T(np.array([0], np.uint64))
+    args = (bad, one) if not transpose else (one, bad)
+    assert L.hnh_coo_to_csr_device(rows, cols, 1, args[0].data_ptr(), args[1].data_ptr(), dv.data_ptr(), transpose,
+                                   d_rs.data_ptr(), d_ci.data_ptr(), d_ri.data_ptr(), d_v.data_ptr(), st) == -1
