@@ -45,6 +45,8 @@ ABI = {
     "hnh_block_run_host": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_er_generate_host": (C.c_int64, [C.c_int, C.c_int, C.c_uint64, _I64, _I64, _P, _P, _P, _I64]),
     "hnh_coo_to_csr_host": (C.c_int, [_I64, _I64, _I64, _P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    "hnh_sddmm_coo_host": (C.c_int, [_P, _P, _P, _I64, _P, _I64, _P, _I64, C.c_int]),
+    "hnh_spmm_host": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I64, _P, C.c_int]),
     "hnh_er_generate_device": (C.c_int64, [C.c_int, C.c_int, C.c_uint64, _I64, _I64, _P, _P, _P, _I64, _P]),
     "hnh_coo_to_csr_device": (C.c_int, [_I64, _I64, _I64, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
 }

@@ -185,6 +185,18 @@ void hnh_block_destroy(hnh_block_t *blk);
 int hnh_block_run_host(hnh_block_t *blk, int op, const double *X, const double *Y,
                        double *values_io, double *Out, int r, int run_flags, void *stream);
 
+/* One-shot forms with HOST pointers for a reference-side KernelImplementation that keeps the
+ * reference's host data structures (include/hnh/reference_plugin/cuda_kernel.h): operands are
+ * mirrored on the device for the call, the result is copied back, the call synchronises.
+ * hnh_sddmm_coo_host: values[i] += X[row_idx[i]] . Y[col_idx[i]]  (StandardKernel::sddmm_local,
+ * sparse_kernels.cpp:44-55; X has x_rows rows, Y has y_rows rows, both r wide).
+ * hnh_spmm_host: Y[rows x r] += CSR * X  (the mkl_sparse_d_mm call, sparse_kernels.cpp:95-120;
+ * X has x_rows rows). */
+int hnh_sddmm_coo_host(const int64_t *row_idx, const int64_t *col_idx, double *values, int64_t nnz,
+                       const double *X, int64_t x_rows, const double *Y, int64_t y_rows, int r);
+int hnh_spmm_host(const int64_t *rowStart, const int64_t *col_idx, const double *values,
+                  int64_t rows, int64_t nnz, const double *X, int64_t x_rows, double *Y, int r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,10 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libhnh_ref.so")
+# the same reference code with this repo's CUDA kernels plugged in through KernelImplementation (ref.mk `cuda`)
+SO_CUDA = os.path.join(_HERE, "_ref", "libhnh_ref_cuda.so")
 _LIB = None
+_LIB_CUDA = None
 
 
 def available() -> bool:
@@ -26,48 +29,63 @@ def available() -> bool:
 def build() -> bool:
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", _HERE, "-f", "ref.mk"], stdout=subprocess.DEVNULL)
+        build_cuda_plugin()
     return available()
 
 
-def lib():
-    global _LIB
+def build_cuda_plugin() -> bool:
+    """Optional second build: needs the product library (distributed_sddmm_b200/libhnh_b200.so) to link against."""
+    if os.path.isdir("/root/reference"):
+        subprocess.call(["make", "-C", _HERE, "-f", "ref.mk", "cuda"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return os.path.exists(SO_CUDA)
+
+
+def lib(plugin: bool = False):
+    global _LIB, _LIB_CUDA
+    if plugin:
+        if _LIB_CUDA is None:
+            _LIB_CUDA = _bind(C.CDLL(SO_CUDA))
+        return _LIB_CUDA
     if _LIB is None:
-        L = C.CDLL(SO)
-        P = C.c_void_p
-        L.ref_run.restype = P
-        L.ref_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P, P,
-                              C.c_char_p, C.c_int]
-        L.ref_error.restype = C.c_char_p
-        L.ref_error.argtypes = [P]
-        L.ref_free.argtypes = [P]
-        L.ref_rank_info.argtypes = [P, C.c_int, P]
-        for name in ("ref_submatrices",):
-            getattr(L, name).restype = P
-            getattr(L, name).argtypes = [P, C.c_int, C.c_int]
-        L.ref_num_values.restype = C.c_int64
-        L.ref_num_values.argtypes = [P, C.c_int, C.c_int]
-        for name in ("ref_value_rows", "ref_value_cols"):
-            getattr(L, name).restype = P
-            getattr(L, name).argtypes = [P, C.c_int, C.c_int]
-        L.ref_block_meta.argtypes = [P, C.c_int, C.c_int, C.c_int, P]
-        for name in ("ref_block_rowStart", "ref_block_col_idx", "ref_block_row_idx", "ref_block_values"):
-            getattr(L, name).restype = P
-            getattr(L, name).argtypes = [P, C.c_int, C.c_int, C.c_int]
-        for name in ("ref_op_A", "ref_op_B", "ref_op_values"):
-            getattr(L, name).restype = P
-            getattr(L, name).argtypes = [P, C.c_int, C.c_int]
-        L.ref_op_num_values.restype = C.c_int64
-        L.ref_op_num_values.argtypes = [P, C.c_int, C.c_int]
-        L.ref_op_elapsed.restype = C.c_double
-        L.ref_op_elapsed.argtypes = [P, C.c_int, C.c_int]
-        L.ref_benchmark.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
-                                    C.c_char_p, C.c_char_p, C.c_int]
-        L.ref_benchmark.restype = None
-        L.ref_time_fused.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
-                                     C.c_int, P]
-        L.ref_time_fused.restype = C.c_int64
-        _LIB = L
+        _LIB = _bind(C.CDLL(SO))
     return _LIB
+
+
+def _bind(L):
+    P = C.c_void_p
+    L.ref_run.restype = P
+    L.ref_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P, P,
+                          C.c_char_p, C.c_int]
+    L.ref_error.restype = C.c_char_p
+    L.ref_error.argtypes = [P]
+    L.ref_free.argtypes = [P]
+    L.ref_rank_info.argtypes = [P, C.c_int, P]
+    for name in ("ref_submatrices",):
+        getattr(L, name).restype = P
+        getattr(L, name).argtypes = [P, C.c_int, C.c_int]
+    L.ref_num_values.restype = C.c_int64
+    L.ref_num_values.argtypes = [P, C.c_int, C.c_int]
+    for name in ("ref_value_rows", "ref_value_cols"):
+        getattr(L, name).restype = P
+        getattr(L, name).argtypes = [P, C.c_int, C.c_int]
+    L.ref_block_meta.argtypes = [P, C.c_int, C.c_int, C.c_int, P]
+    for name in ("ref_block_rowStart", "ref_block_col_idx", "ref_block_row_idx", "ref_block_values"):
+        getattr(L, name).restype = P
+        getattr(L, name).argtypes = [P, C.c_int, C.c_int, C.c_int]
+    for name in ("ref_op_A", "ref_op_B", "ref_op_values"):
+        getattr(L, name).restype = P
+        getattr(L, name).argtypes = [P, C.c_int, C.c_int]
+    L.ref_op_num_values.restype = C.c_int64
+    L.ref_op_num_values.argtypes = [P, C.c_int, C.c_int]
+    L.ref_op_elapsed.restype = C.c_double
+    L.ref_op_elapsed.argtypes = [P, C.c_int, C.c_int]
+    L.ref_benchmark.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int,
+                                C.c_char_p, C.c_char_p, C.c_int]
+    L.ref_benchmark.restype = None
+    L.ref_time_fused.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                 C.c_int, P]
+    L.ref_time_fused.restype = C.c_int64
+    return L
 
 
 def _arr(ptr, n, dtype):
@@ -78,11 +96,14 @@ def _arr(ptr, n, dtype):
                                  shape=(n,)).copy()
 
 
-def run(alg: str, p: int, c: int, R: int, M: int, N: int, rows, cols, vals, A, B, script, threads_per_rank: int = 1):
+def run(alg: str, p: int, c: int, R: int, M: int, N: int, rows, cols, vals, A, B, script, threads_per_rank: int = 1,
+        plugin: bool = False):
     """Run `script` (list of ops) of the reference's `alg` on p thread-ranks.  rows/cols/vals must be
     sorted by (row, col).  Returns a list (one per rank) of dicts with the layout, the local CSR
-    blocks, the global coordinates of every local value slot and the per-op local outputs."""
-    L = lib()
+    blocks, the global coordinates of every local value slot and the per-op local outputs.
+    plugin=True: the build whose local kernels are this repo's CUDA kernels behind the reference's
+    KernelImplementation interface (needs a GPU)."""
+    L = lib(plugin)
     rows = np.ascontiguousarray(rows, np.uint64)
     cols = np.ascontiguousarray(cols, np.uint64)
     vals = np.ascontiguousarray(vals, np.float64)

@@ -28,6 +28,16 @@
 
 uint64_t hnh_shim_er_seed = 0xC0FFEEull;
 
+// -DHNH_CUDA_PLUGIN builds oracle/_ref/libhnh_ref_cuda.so: the same reference code with ONE change, the one a
+// maintainer would make (INTEGRATION.md route B) -- the local kernels come from libhnh_b200.so through the
+// reference's own plugin interface instead of StandardKernel (MKL shim + OpenMP loop).
+#ifdef HNH_CUDA_PLUGIN
+#include "hnh/reference_plugin/cuda_kernel.h"
+typedef CudaKernel LocalKernel;
+#else
+typedef StandardKernel LocalKernel;
+#endif
+
 namespace {
 
 struct BlockDump {
@@ -148,7 +158,7 @@ void rank_main(int rank, void *arg) {
     for (int64_t t = lo; t < hi; t++) S.coords[(size_t)(t - lo)] = spcoord_t{J.rows[t], J.cols[t], J.vals[t]};
     S.M = (uint64_t)J.M; S.N = (uint64_t)J.N; S.dist_nnz = (uint64_t)J.nnz; S.initialized = true;
 
-    StandardKernel kernel;
+    LocalKernel kernel;
     Distributed_Sparse *d = make_alg(J.alg, &S, J.R, J.c, &kernel);
     if (!d) { std::lock_guard<std::mutex> lk(J.mu); J.error = "unknown algorithm " + J.alg; return; }
     O.i = d->grid->i; O.j = d->grid->j; O.k = d->grid->k;
