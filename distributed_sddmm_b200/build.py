@@ -79,7 +79,9 @@ def build_reference_driver() -> str | None:
         return None
     exe = _compile_reference_main(src, "bench_er_reference_main")
     # the reference's two other drivers (MatrixMarket file input; sweep over R), same recipe
-    for other, name in (("bench_file.cpp", "bench_file_reference_main"), ("bench_heatmap.cpp", "bench_heatmap_reference_main")):
+    # ... and its self-check program (fingerprints of sddmmA / spmmA / spmmB on dummyInitialize inputs, then a GAT pass)
+    for other, name in (("bench_file.cpp", "bench_file_reference_main"), ("bench_heatmap.cpp", "bench_heatmap_reference_main"),
+                        ("scratch.cpp", "scratch_reference_main")):
         path = os.path.join("/root/reference", other)
         if os.path.exists(path):
             try:

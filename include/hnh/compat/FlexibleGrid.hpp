@@ -2,3 +2,4 @@
 // against the B200-native library.  See INTEGRATION.md.
 #pragma once
 #include "hnh/FlexibleGrid.hpp"
+#include "mpi_standins.h"

@@ -2,3 +2,4 @@
 // against the B200-native library.  See INTEGRATION.md.
 #pragma once
 #include "hnh/als_conjugate_gradients.h"
+#include "mpi_standins.h"

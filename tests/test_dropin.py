@@ -16,7 +16,8 @@ def test_reference_driver_compiles_unchanged():
     from distributed_sddmm_b200 import build
     exe = build.build_reference_driver()
     assert exe and os.path.exists(exe)
-    for other in ("bench_file_reference_main", "bench_heatmap_reference_main"):  # bench_file.cpp, bench_heatmap.cpp
+    # bench_file.cpp, bench_heatmap.cpp, scratch.cpp
+    for other in ("bench_file_reference_main", "bench_heatmap_reference_main", "scratch_reference_main"):
         assert os.path.exists(os.path.join(PKG, other)), other
     import torch
     if not torch.cuda.is_available():
@@ -64,3 +65,41 @@ def test_reference_file_driver_runs_on_gpu(tmp_path):
     records = json.loads("[" + out.read_text().strip().rstrip(",") + "]")
     assert [r["alg_name"] for r in records] == ["15d_sparse"] and records[0]["fused"] is False
     assert records[0]["alg_info"]["nnz"] == len(rows) and records[0]["overall_throughput"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+def test_reference_self_check_program_runs_on_gpu(tmp_path):
+    """The reference's scratch.cpp -- its only self-check: squared-norm fingerprints of sddmmA / spmmA / spmmB on
+    dummyInitialize inputs with the 1.5D sparse-shift algorithm, then a GAT forward pass -- compiled unchanged.
+    The reference prints the fingerprints without expected values; here they are compared with
+    scipy on the global matrices (X[i, j] = i * R + j, distributed_sparse.h:322-346)."""
+    path = os.path.join(PKG, "scratch_reference_main")
+    if not os.path.exists(path):
+        pytest.skip("scratch_reference_main not built")
+    import numpy as np
+    import scipy.sparse as sp
+    from oracle import hnh_oracle as orc
+    logM, R = 8, 8
+    N = 1 << logM
+    rows, cols, _ = orc.er_tuples(logM, 6, 5)
+    mtx = tmp_path / "er.mtx"
+    with open(mtx, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n")
+        f.write(f"{N} {N} {len(rows)}\n")
+        np.savetxt(f, np.column_stack([rows + 1, cols + 1, np.ones(len(rows))]), fmt="%d %d %g")
+    p = subprocess.run([path, str(mtx), str(R), "1"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    got = {}
+    for line in p.stdout.splitlines():
+        if "Fingerprint:" in line:
+            k, v = line.split("Fingerprint:")
+            got[k.strip()] = float(v)
+    X = orc.dummy_matrix(0, N, R)
+    S = sp.csr_matrix((np.ones(len(rows)), (rows.astype(np.int64), cols.astype(np.int64))), shape=(N, N))
+    S.sort_indices()
+    ri = np.repeat(np.arange(N), np.diff(S.indptr))
+    want = {"SDDMM": float((np.einsum("ij,ij->i", X[ri], X[S.indices]) ** 2).sum()),
+            "SpMMA": float(((S @ X) ** 2).sum()), "SpMMB": float(((S.T @ X) ** 2).sum())}
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-5 * v, (k, got[k], v)  # the program prints 6 significant digits
