@@ -29,8 +29,10 @@ def test_load_er_matches_oracle(world):
 
 @pytest.mark.parametrize("name,transposed", [("15d_fusion1", True), ("15d_fusion2", False), ("15d_sparse", False),
                                              ("25d_dense_replicate", True), ("25d_sparse_replicate", False)])
-def test_p1_layout_and_blocks(world, name, transposed):
-    logM, npr, R = 9, 6, 16
+# (14, 40): 650k tuples -- the multi-threaded paths of the tuple bucketing and of the CSR counting sort (host_sort.h)
+@pytest.mark.parametrize("logM,npr", [(9, 6), (14, 40)])
+def test_p1_layout_and_blocks(world, name, transposed, logM, npr):
+    R = 16
     N = 1 << logM
     S = D.SpmatLocal.load_er(logM, npr, SEED)
     rows, cols, vals = orc.er_tuples(logM, npr, SEED)

@@ -59,3 +59,32 @@ def test_coo_to_csr_host_matches_oracle(hnh, transpose):
     bad = np.array([M], np.uint64)
     assert hnh.hnh_coo_to_csr_host(M, N, 1, bad.ctypes.data, bad.ctypes.data, v.ctypes.data, 0,
                                    rs.ctypes.data, ci.ctypes.data, None, vv.ctypes.data) == -1
+
+
+@pytest.mark.parametrize("transpose", [False, True])
+@pytest.mark.parametrize("shape", ["wide", "one_row", "sparse_rows"])
+def test_coo_to_csr_host_parallel_path_matches_oracle(hnh, transpose, shape):
+    """Enough entries for the multi-threaded histogram path of the stable counting sort (csrc/host_sort.h): every
+    thread's chunk must land behind the previous thread's entries of the same row, duplicates in input order."""
+    rng = np.random.default_rng(23)
+    nnz = 600_000
+    M, N = {"wide": (5000, 3000), "one_row": (1, 4096), "sparse_rows": (1 << 20, 1 << 10)}[shape]
+    if transpose and shape == "one_row":
+        M, N = N, M
+    r = rng.integers(0, M, nnz).astype(np.uint64)
+    c = rng.integers(0, N, nnz).astype(np.uint64)
+    order = np.lexsort((r, c))
+    r, c = np.ascontiguousarray(r[order]), np.ascontiguousarray(c[order])
+    v = np.arange(nnz, dtype=np.float64)  # distinct values: the order of duplicates is observable
+    ref = orc.coo_to_csr(M, N, r, c, v, transpose=transpose)
+    out_rows = N if transpose else M
+    rs, ci, ri, vv = np.zeros(out_rows + 1, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz, np.int64), np.zeros(nnz)
+    assert hnh.hnh_coo_to_csr_host(M, N, nnz, r.ctypes.data, c.ctypes.data, v.ctypes.data, int(transpose), rs.ctypes.data,
+                                   ci.ctypes.data, ri.ctypes.data, vv.ctypes.data) == 0
+    assert np.array_equal(rs, ref.rowStart) and np.array_equal(ci, ref.col_idx)
+    assert np.array_equal(ri, ref.row_idx) and np.array_equal(vv, ref.values)
+    # one bad coordinate in the last thread's chunk is still found
+    r2 = r.copy()
+    r2[-3] = M + 7
+    assert hnh.hnh_coo_to_csr_host(M, N, nnz, r2.ctypes.data, c.ctypes.data, v.ctypes.data, int(transpose), rs.ctypes.data,
+                                   ci.ctypes.data, ri.ctypes.data, vv.ctypes.data) == -1
