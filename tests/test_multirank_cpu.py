@@ -17,6 +17,9 @@ CASES_2 = [
     # sizes that do not divide evenly: trailing blocks are padded (ceil-div sizing, common.cpp:20-27)
     U.case("15d_fusion2", 1, 8, 7, 5, n=101),
     U.case("15d_sparse", 1, 8, 7, 5, n=101),
+    # 650k tuples: the multi-threaded bucketing / counting-sort paths of the setup (needs oracle/_ref; no golden file)
+    U.case("15d_fusion1", 1, 8, 14, 40, name="nogolden_big_fusion1"),
+    U.case("25d_sparse_replicate", 2, 8, 14, 40, name="nogolden_big_25d_sparse"),
 ]
 CASES_4 = [
     U.case("15d_fusion1", 2, 8, 7, 5),
