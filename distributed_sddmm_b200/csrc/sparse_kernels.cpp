@@ -45,13 +45,14 @@ size_t StandardKernel::spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B,
 }
 
 void StandardKernel::fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block,
-                                      int64_t row0, int64_t nrows) {
+                                      int64_t row0, int64_t nrows, bool out_is_zero) {
     CSRLocal *blk = S.csr_blocks[block];
     if (nrows <= 0) return;
     const int64_t r = X.cols();
     if (blk == nullptr || blk->num_coords == 0) {
-        hnh::cuda_check(cudaMemsetAsync(Out.data() + row0 * r, 0, sizeof(double) * (size_t)(nrows * r),
-                                        Runtime::get().compute_stream()), "cudaMemsetAsync");
+        if (out_is_zero)
+            hnh::cuda_check(cudaMemsetAsync(Out.data() + row0 * r, 0, sizeof(double) * (size_t)(nrows * r),
+                                            Runtime::get().compute_stream()), "cudaMemsetAsync");
         return;
     }
     if (blk->transpose) throw hnh::Error(HNH_E_MODE, "fused_local_rows needs a non-transposed block");
@@ -61,7 +62,8 @@ void StandardKernel::fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix
     // rowStart / X / Out pointers
     abi_check(hnh_fused_f64(h->rowStart.data() + row0, h->col_idx.data(), h->values.data(), nrows, blk->num_coords,
                             X.data() + row0 * r, B.data(), Out.data() + row0 * r, (int)r,
-                            flags | HNH_FLAG_BETA0_VALUES | HNH_FLAG_BETA0_OUT, Runtime::get().compute_stream()),
+                            flags | HNH_FLAG_BETA0_VALUES | (out_is_zero ? HNH_FLAG_BETA0_OUT : 0),
+                            Runtime::get().compute_stream()),
               "hnh_fused_f64");
 }
 

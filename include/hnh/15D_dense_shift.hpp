@@ -187,16 +187,25 @@ public:
         }
     }
 
-    // Host-operand FusedMM.  On one rank with local kernel fusion the result row i depends on A row i and on
-    // all of B only, so the rows of the stationary operand are streamed: chunk t+1 is uploading and chunk
-    // t-1 is downloading (the two PCIe directions) while the fused kernel works on chunk t.  The end-to-end
-    // time drops from H2D(A) + H2D(B) + kernel + D2H(out) to about H2D(B) + H2D(A) + one chunk.
+    // Host-operand FusedMM.  With local kernel fusion the result row i depends on row i of the stationary operand
+    // and on the riding operand only, so the rows of the stationary operand are streamed: chunk t+1 is uploading
+    // and chunk t-1 is downloading (the two PCIe directions) while the fused kernel works on chunk t.  The
+    // end-to-end time drops from H2D(A) + H2D(B) + kernels + D2H(out) to about the two uploads plus one chunk.
+    // One rank: in place, one kernel per chunk.  Several ranks (c = 1): the riding shards are all-gathered over the
+    // ring's communicator while the stationary operand uploads, and every chunk visits all p blocks before it
+    // leaves -- the row chunk is the outer loop, the block the inner one.
     int64_t host_pipeline_chunk_rows = 1 << 15;
     void fusedSpMM_host(const double *hostA, const double *hostB, double *hostOut, DenseMatrix &localA,
                         DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer, MatMode mode) override {
         StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
-        if (fusionApproach != 2 || p != 1 || sk == nullptr || host_pipeline_chunk_rows <= 0) {
+        if (fusionApproach != 2 || c != 1 || sk == nullptr || host_pipeline_chunk_rows <= 0) {
             Distributed_Sparse::fusedSpMM_host(hostA, hostB, hostOut, localA, localB, Svalues, sddmm_buffer, mode);
+            return;
+        }
+        if (p > 1) {
+            fusedSpMM_host_gathered(mode == Amat ? hostA : hostB, mode == Amat ? hostB : hostA, hostOut,
+                                    mode == Amat ? localA : localB, mode == Amat ? localB : localA,
+                                    mode == Amat ? S.get() : ST.get(), sk);
             return;
         }
         hnh::Runtime &rt = hnh::Runtime::get();
@@ -230,6 +239,51 @@ public:
     }
 
 private:
+    // p > 1, c = 1: see fusedSpMM_host.  Block b of this rank's block row multiplies the shard owned by rank b of
+    // the column communicator (block_at(step) with c = 1 is (rankInCol - step) mod p, the owner of the shard the
+    // ring would deliver at that step), so the all-gathered riding operand is indexed by block id.
+    void fusedSpMM_host_gathered(const double *h_stationary, const double *h_riding, double *hostOut,
+                                 DenseMatrix &stationary, DenseMatrix &riding, SpmatLocal *choice, StandardKernel *sk) {
+        hnh::Runtime &rt = hnh::Runtime::get();
+        cudaStream_t in = rt.copy_in_stream(), out = rt.copy_out_stream();
+        const int64_t rows = stationary.rows(), r = stationary.cols(), shard_rows = riding.rows();
+
+        rt.chain(compute(), in);
+        if (riding.size())
+            hnh::cuda_check(cudaMemcpyAsync(riding.data(), h_riding, sizeof(double) * (size_t)riding.size(),
+                                            cudaMemcpyHostToDevice, in), "h2d riding operand");
+        gathered_riding.resize(shard_rows * p, r);
+        rt.chain(in, comm());
+        rt.chain(compute(), comm());  // earlier readers of the gather buffer
+        region_begin("Cyclic Shift Time", comm());
+        grid->col_world->allgather(riding.data(), gathered_riding.data(), sizeof(double) * (size_t)riding.size(), comm());
+        region_end("Cyclic Shift Time", comm());
+        rt.chain(comm(), compute());
+        accumulation_buffer.resize(rows, r);
+
+        for (int64_t row0 = 0; row0 < rows; row0 += host_pipeline_chunk_rows) {
+            const int64_t n = std::min(host_pipeline_chunk_rows, rows - row0);
+            const size_t bytes = sizeof(double) * (size_t)(n * r);
+            hnh::cuda_check(cudaMemcpyAsync(stationary.data() + row0 * r, h_stationary + row0 * r, bytes,
+                                            cudaMemcpyHostToDevice, in), "h2d stationary rows");
+            rt.chain(in, compute());
+            region_begin("Computation Time", compute());
+            for (int step = 0; step < p; step++) {
+                const int b = block_at(step);
+                DenseMatrix shard = gathered_riding.rowsView((int64_t)b * shard_rows, shard_rows);
+                sk->fused_local_rows(*choice, stationary, shard, accumulation_buffer, b, row0, n, step == 0);
+            }
+            region_end("Computation Time", compute());
+            rt.chain(compute(), out);
+            hnh::cuda_check(cudaMemcpyAsync(hostOut + row0 * r, accumulation_buffer.data() + row0 * r, bytes,
+                                            cudaMemcpyDeviceToHost, out), "d2h result rows");
+        }
+        rt.chain(out, compute());
+        hnh::cuda_check(cudaStreamSynchronize(out), "fusedSpMM_host");
+        stationary.swap(accumulation_buffer);  // the staging matrix holds the result, as after fusedSpMM
+    }
+    DenseMatrix gathered_riding;  // all p shards of the riding operand (fusedSpMM_host, p > 1)
+
     static void localise(SpmatLocal &m, int block_rows, int block_cols) {
 #pragma omp parallel for
         for (int64_t i = 0; i < (int64_t)m.coords.size(); i++) m.coords[i].r %= (uint64_t)block_rows;

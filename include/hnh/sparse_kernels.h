@@ -69,8 +69,9 @@ public:
     size_t spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B, MatMode mode, int block) override;
     size_t fused_local(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block, bool first_visit,
                        bool out_is_zero) override;
-    // fused_local restricted to the CSR rows [row0, row0 + nrows) of the block, overwriting both the block's
-    // values and those rows of Out (Out may be X): the unit of the host-operand pipeline (fusedSpMM_host).
+    // fused_local restricted to the CSR rows [row0, row0 + nrows) of the block: the unit of the host-operand
+    // pipeline (fusedSpMM_host).  The block's values of those rows are overwritten (first visit); the rows of
+    // Out are overwritten when out_is_zero (Out may then be X), accumulated into otherwise.
     void fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block, int64_t row0,
-                          int64_t nrows);
+                          int64_t nrows, bool out_is_zero = true);
 };

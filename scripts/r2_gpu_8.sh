@@ -10,3 +10,4 @@ done
 LOGM=22 NPR=64 R=32 ALGS=15d_sparse CS=1,8 timeout 300 $T scripts/scale_sweep.py > gpurun_out/r2_sweep8_cfg3.log 2>&1; grep '^{' gpurun_out/r2_sweep8_cfg3.log | cut -c1-400
 LOGM=20 NPR=32 R=256 ALGS=25d_dense_replicate,25d_sparse_replicate CS=2 timeout 300 $T scripts/scale_sweep.py > gpurun_out/r2_sweep8_cfg4.log 2>&1; grep '^{' gpurun_out/r2_sweep8_cfg4.log | cut -c1-400
 timeout 300 $T bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench8.json 2> gpurun_out/r2_bench8.err; tail -c 800 gpurun_out/r2_bench8.json
+timeout 300 $T bench.py --gpus 8 --steps 10 --warmup 3 --e2e-pipeline > gpurun_out/r2_bench8_pipe.json 2> gpurun_out/r2_bench8_pipe.err; tail -c 500 gpurun_out/r2_bench8_pipe.json

@@ -147,6 +147,23 @@ def main():
             out["perf"] = json.dumps(alg.perf())
             if case.get("als"):
                 out["als"] = np.array(alg.als_residuals(1))
+        if have_gpu and case.get("hostpipe"):
+            # fusedSpMM_host (upload / kernels / download pipelined, riding operand all-gathered) against the device path
+            A, B = alg.like_A_matrix(), alg.like_B_matrix()
+            GA, GB = global_inputs(N, R, seed)
+            shapeA, shapeB = (d.localArows, d.localAcols), (d.localBrows, d.localBcols)
+            hA = gather_local(GA, alg.submatrices("A"), shapeA)
+            hB = gather_local(GB, alg.submatrices("B"), shapeB)
+            for mode, like in (("A", alg.like_S_values), ("B", alg.like_ST_values)):
+                Sv, res = like(1.0), like(0.0)
+                A.from_host(hA)
+                B.from_host(hB)
+                alg.fusedSpMM(A, B, Sv, res, mode)
+                out[f"hostpipe_{mode}_want"] = (A if mode == "A" else B).to_host()
+                got = np.full(shapeA if mode == "A" else shapeB, np.nan)
+                alg.fusedSpMM_host(A, B, Sv, res, hA, hB, got, mode, chunk_rows=case["hostpipe"])
+                out[f"hostpipe_{mode}_got"] = got
+                out[f"hostpipe_{mode}_staged"] = (A if mode == "A" else B).to_host()
         if have_gpu and case.get("gat"):
             # GAT forward pass on this algorithm object (dense-shift layouts: one row block per rank, full width)
             g = case["gat"]

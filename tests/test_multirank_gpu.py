@@ -99,3 +99,28 @@ def test_gat_forward_matches_reference(nproc):
             assert have.shape == want.shape, (c["name"], r, have.shape, want.shape)
             err = np.abs(have - want).max() / max(np.abs(want).max(), 1e-300)
             assert err < 1e-11, (c["name"], r, err)
+
+
+HOSTPIPE_CASES = {
+    2: [dict(U.case("15d_fusion2", 1, 8, 7, 5, script=[], name="hostpipe_c1_chunk24"), hostpipe=24),
+        dict(U.case("15d_fusion2", 1, 8, 7, 5, script=[], name="hostpipe_c1_default"), hostpipe=0),
+        dict(U.case("15d_fusion2", 2, 8, 7, 5, script=[], name="hostpipe_c2_plain"), hostpipe=16),   # c > 1: plain copy-in / copy-out
+        dict(U.case("15d_fusion1", 1, 8, 7, 5, script=[], name="hostpipe_fusion1_plain"), hostpipe=16)],
+    4: [dict(U.case("15d_fusion2", 1, 8, 7, 5, script=[], name="hostpipe_c1_chunk8"), hostpipe=8),
+        dict(U.case("15d_fusion2", 1, 8, 7, 5, script=[], name="hostpipe_c1_n99", n=99), hostpipe=8)],
+}
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_fused_host_operands_multirank(nproc):
+    """Distributed_Sparse::fusedSpMM_host on several ranks: bit-identical with upload + fusedSpMM + download (the blocks
+    of a row are visited in the ring's order), for both modes, and the staging matrix ends up holding the result."""
+    cases = HOSTPIPE_CASES[nproc]
+    got = U.run_cases(nproc, cases, transport_for(nproc), timeout=900)
+    for c in cases:
+        for r, rank_out in enumerate(got[c["name"]]):
+            for mode in ("A", "B"):
+                want = rank_out[f"hostpipe_{mode}_want"]
+                assert np.array_equal(rank_out[f"hostpipe_{mode}_got"], want), (c["name"], r, mode)
+                assert np.array_equal(rank_out[f"hostpipe_{mode}_staged"], want), (c["name"], r, mode)
