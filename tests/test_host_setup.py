@@ -88,3 +88,36 @@ def test_coo_to_csr_host_parallel_path_matches_oracle(hnh, transpose, shape):
     r2[-3] = M + 7
     assert hnh.hnh_coo_to_csr_host(M, N, nnz, r2.ctypes.data, c.ctypes.data, v.ctypes.data, int(transpose), rs.ctypes.data,
                                    ci.ctypes.data, ri.ctypes.data, vv.ctypes.data) == -1
+
+
+def test_coo_to_csr_host_random_shapes_property(hnh):
+    """Property test over small random blocks (including empty ones, single rows / columns, heavy duplication):
+    the host COO -> CSR equals the oracle's, rowStart is a monotone partition of [0, nnz], and transposing twice
+    returns the original entries."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.integers(1, 40), st.integers(0, 300), st.booleans(), st.integers(0, 2 ** 31))
+    def check(M, N, nnz, transpose, seed):
+        rng = np.random.default_rng(seed)
+        r = rng.integers(0, M, nnz).astype(np.uint64)
+        c = rng.integers(0, N, nnz).astype(np.uint64)
+        order = np.lexsort((r, c))
+        r, c = np.ascontiguousarray(r[order]), np.ascontiguousarray(c[order])
+        v = rng.uniform(-1, 1, nnz)
+        out_rows = N if transpose else M
+        rs = np.full(out_rows + 1, -1, np.int64)
+        ci, ri, vv = np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1), np.int64), np.zeros(max(nnz, 1))
+        assert hnh.hnh_coo_to_csr_host(M, N, nnz, r.ctypes.data, c.ctypes.data, v.ctypes.data, int(transpose), rs.ctypes.data,
+                                       ci.ctypes.data, ri.ctypes.data, vv.ctypes.data) == 0
+        assert rs[0] == 0 and rs[-1] == nnz and np.all(np.diff(rs) >= 0)
+        if nnz:
+            ref = orc.coo_to_csr(M, N, r, c, v, transpose=transpose)
+            assert np.array_equal(rs, ref.rowStart) and np.array_equal(ci[:nnz], ref.col_idx)
+            assert np.array_equal(ri[:nnz], ref.row_idx) and np.array_equal(vv[:nnz], ref.values)
+            # the multiset of (row, col, value) is preserved
+            a = sorted(zip((c if transpose else r).tolist(), (r if transpose else c).tolist(), v.tolist()))
+            b = sorted(zip(ri[:nnz].tolist(), ci[:nnz].tolist(), vv[:nnz].tolist()))
+            assert a == b
+
+    check()
