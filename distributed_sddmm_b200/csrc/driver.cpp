@@ -348,6 +348,41 @@ int hnhd_als_residuals(hnhd_alg_t *a, int steps, double *out2) {
     });
 }
 
+int hnhd_als_run(hnhd_alg_t *a, const double *hostAgt, const double *hostBgt, const double *hostA0, const double *hostB0,
+                 int steps, int cg_iters, double *out2, double *hostA_out, double *hostB_out) {
+    return guarded([&] {
+        if (!a || !hostAgt || !hostBgt || !hostA0 || !hostB0 || !out2 || steps < 0 || cg_iters < 0)
+            throw hnh::Error(HNH_E_INVALID, "hnhd_als_run: bad argument");
+        Distributed_Sparse *d = a->alg.get();
+        Distributed_ALS als(d, false);
+        DenseMatrix Agt = d->like_A_matrix(0.0), Bgt = d->like_B_matrix(0.0);
+        Agt.copy_from_host(hostAgt);
+        Bgt.copy_from_host(hostBgt);
+        VectorXd ones = d->like_S_values(1.0);
+        als.ground_truth = d->like_S_values(0.0);
+        d->initial_shift(&Agt, &Bgt, k_sddmmA);
+        d->sddmmA(Agt, Bgt, ones, als.ground_truth);
+        d->de_shift(&Agt, &Bgt, k_sddmmA);
+        VectorXd ones_t = d->like_ST_values(1.0);
+        als.ground_truth_transpose = d->like_ST_values(0.0);
+        d->initial_shift(&Agt, &Bgt, k_sddmmB);
+        d->sddmmB(Agt, Bgt, ones_t, als.ground_truth_transpose);
+        d->de_shift(&Agt, &Bgt, k_sddmmB);
+        als.A = d->like_A_matrix(0.0);
+        als.B = d->like_B_matrix(0.0);
+        als.A.copy_from_host(hostA0);
+        als.B.copy_from_host(hostB0);
+        out2[0] = als.computeResidual();
+        for (int i = 0; i < steps; i++) {
+            als.cg_optimizer(Amat, cg_iters);
+            als.cg_optimizer(Bmat, cg_iters);
+        }
+        out2[1] = als.computeResidual();
+        if (hostA_out) als.A.copy_to_host(hostA_out);
+        if (hostB_out) als.B.copy_to_host(hostB_out);
+    });
+}
+
 // ---- GAT ------------------------------------------------------------------------------------------
 int hnhd_gat_create(hnhd_alg_t *a, int n_layers, const int *layers3, double alpha, hnhd_gat_t **out) {
     return guarded([&] {

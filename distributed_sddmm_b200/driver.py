@@ -372,3 +372,14 @@ class GAT:
             lib().hnhd_gat_destroy(self.h)
         except Exception:
             pass
+
+
+def als_run(alg: Algorithm, Agt, Bgt, A0, B0, steps: int = 1, cg_iters: int = 10):
+    """Distributed_ALS on caller inputs (this rank's local shards, numpy float64): ground truth from (Agt, Bgt),
+    embeddings (A0, B0), `steps` alternating cg_optimizer rounds.  Returns ((residual before, after), A, B)."""
+    mats = [np.ascontiguousarray(m, dtype=np.float64) for m in (Agt, Bgt, A0, B0)]
+    res = (C.c_double * 2)()
+    outA, outB = np.empty_like(mats[2]), np.empty_like(mats[3])
+    check(lib().hnhd_als_run(alg.h, *[m.ctypes.data for m in mats], steps, cg_iters, res, outA.ctypes.data, outB.ctypes.data),
+          "hnhd_als_run")
+    return (res[0], res[1]), outA, outB

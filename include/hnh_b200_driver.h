@@ -163,6 +163,15 @@ int hnhd_benchmark_algorithm(hnhd_spmat_t *S, const char *algorithm_name, const 
  * out2 = {residual before, residual after} (world-reduced, identical on every rank).  Collective. */
 int hnhd_als_residuals(hnhd_alg_t *alg, int steps, double *out2);
 
+/* The same alternating rounds on CALLER inputs, for parity tests against the reference's Distributed_ALS: ground
+ * truth = SDDMM of the local shards hostAgt / hostBgt over the all-ones pattern (as the constructor builds it,
+ * als_conjugate_gradients.cpp:166-186), embeddings = hostA0 / hostB0 (instead of initializeEmbeddings()'s random
+ * draw), `steps` rounds of cg_optimizer(Amat, cg_iters); cg_optimizer(Bmat, cg_iters).  out2 = residual before /
+ * after; hostA_out / hostB_out (may be NULL) receive the local embeddings.  Collective. */
+int hnhd_als_run(hnhd_alg_t *alg, const double *hostAgt, const double *hostBgt, const double *hostA0,
+                 const double *hostB0, int steps, int cg_iters, double *out2, double *hostA_out,
+                 double *hostB_out);
+
 /* ---- GAT forward pass (include/hnh/gat.hpp; reference gat.hpp:26-113) -----------------------
  * layers3: n_layers triples (input_features, features_per_head, num_heads).  The object keeps a
  * pointer to `alg`, which must outlive it.  buffer 0 is the network input, buffer i + 1 the output

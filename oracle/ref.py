@@ -237,3 +237,54 @@ def gat(alg, p, c, N, rows, cols, vals, layers, weights, alpha, X0, threads_per_
         return G, per_rank
     finally:
         L.ref_gat_free(h)
+
+
+def als(alg, p, c, R, N, rows, cols, Agt, Bgt, A0, B0, steps: int = 1, cg_iters: int = 10, threads_per_rank: int = 1):
+    """The REFERENCE's Distributed_ALS on caller inputs (global N x R matrices; see ref_driver.cpp::ref_als).
+    Returns dict(residual=(before, after), A=global A, B=global B, ranks=[(localA, localB)])."""
+    L = lib()
+    P = C.c_void_p
+    L.ref_als.restype = P
+    L.ref_als.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, P, P, P, P, P, P, P, C.c_int,
+                          C.c_int, C.c_int]
+    L.ref_als_error.restype = C.c_char_p
+    L.ref_als_error.argtypes = [P]
+    L.ref_als_residuals.argtypes = [P, P]
+    L.ref_als_shape_len.argtypes = [P, C.c_int]
+    for name in ("ref_als_shape", "ref_als_A", "ref_als_B"):
+        getattr(L, name).restype = P
+        getattr(L, name).argtypes = [P, C.c_int]
+    L.ref_als_free.argtypes = [P]
+    rows = np.ascontiguousarray(rows, np.uint64)
+    cols = np.ascontiguousarray(cols, np.uint64)
+    vals = np.ones(len(rows))
+    mats = [np.ascontiguousarray(m, np.float64) for m in (Agt, Bgt, A0, B0)]
+    h = L.ref_als(alg.encode(), p, c, R, N, N, len(rows), rows.ctypes.data, cols.ctypes.data, vals.ctypes.data,
+                  *[m.ctypes.data for m in mats], steps, cg_iters, threads_per_rank)
+    try:
+        err = L.ref_als_error(h).decode()
+        if err:
+            raise RuntimeError(err)
+        res = (C.c_double * 2)()
+        L.ref_als_residuals(h, res)
+        GA, GB = np.zeros((N, R)), np.zeros((N, R))
+        ranks = []
+        for rank in range(p):
+            sh = _arr(L.ref_als_shape(h, rank), L.ref_als_shape_len(h, rank), np.int32)
+            lAr, lAc, lBr, lBc, na, nb = (int(x) for x in sh[:6])
+            subsA = sh[6:6 + 4 * na].reshape(na, 4)
+            subsB = sh[6 + 4 * na:6 + 4 * (na + nb)].reshape(nb, 4)
+            locA = _arr(L.ref_als_A(h, rank), lAr * lAc, np.float64).reshape(lAr, lAc)
+            locB = _arr(L.ref_als_B(h, rank), lBr * lBc, np.float64).reshape(lBr, lBc)
+            ranks.append((locA, locB))
+            for G, loc, subs in ((GA, locA, subsA), (GB, locB, subsB)):
+                at, flat = 0, loc.reshape(-1)
+                for top, left, nr, nc in subs:
+                    blk = flat[at:at + nr * nc].reshape(nr, nc)
+                    at += nr * nc
+                    hi = min(top + nr, N)
+                    if hi > top:
+                        G[top:hi, left:left + nc] = blk[:hi - top]
+        return dict(residual=(res[0], res[1]), A=GA, B=GB, ranks=ranks)
+    finally:
+        L.ref_als_free(h)

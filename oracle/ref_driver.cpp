@@ -24,6 +24,7 @@
 #include "common.h"
 #include "distributed_sparse.h"
 #include "gat.hpp"
+#include "als_conjugate_gradients.h"
 #include "sparse_kernels.h"
 
 uint64_t hnh_shim_er_seed = 0xC0FFEEull;
@@ -398,5 +399,86 @@ int ref_gat_shape_len(ref_gat_result *r, int rank) { return (int)r->args.shape[(
 const int *ref_gat_shape(ref_gat_result *r, int rank) { return r->args.shape[(size_t)rank].data(); }
 const double *ref_gat_out(ref_gat_result *r, int rank) { return r->args.out[(size_t)rank].data(); }
 void ref_gat_free(ref_gat_result *r) { delete r; }
+
+
+// The reference's Distributed_ALS / ALS_CG::cg_optimizer (als_conjugate_gradients.cpp:38-141,148-301) on caller
+// inputs: ground truth = SDDMM of (Agt, Bgt) over the all-ones pattern exactly as its constructor computes it
+// (:166-186) but from given matrices instead of Eigen::setRandom(); embeddings A0 / B0 instead of
+// initializeEmbeddings(); `steps` rounds of cg_optimizer(Amat, cg_iters); cg_optimizer(Bmat, cg_iters).
+struct AlsArgs {
+    Job *job;
+    const double *Agt, *Bgt, *A0, *B0;  // global M x R / N x R
+    int steps, cg_iters;
+    std::vector<std::vector<double>> A_out, B_out;
+    std::vector<std::vector<int>> shape;  // localArows, localAcols, localBrows, localBcols, then 4 ints per A / B submatrix
+    double residual[2];
+};
+static void als_main(int rank, void *arg) {
+    AlsArgs &G = *(AlsArgs *)arg;
+    Job &J = *G.job;
+    initialize_mpi_datatypes();
+    SpmatLocal S;
+    const int64_t per = (J.nnz + J.p - 1) / J.p, lo = std::min<int64_t>(per * rank, J.nnz), hi = std::min<int64_t>(lo + per, J.nnz);
+    S.coords.resize((size_t)(hi - lo));
+    for (int64_t t = lo; t < hi; t++) S.coords[(size_t)(t - lo)] = spcoord_t{J.rows[t], J.cols[t], J.vals[t]};
+    S.M = (uint64_t)J.M; S.N = (uint64_t)J.N; S.dist_nnz = (uint64_t)J.nnz; S.initialized = true;
+    StandardKernel kernel;
+    Distributed_Sparse *d = make_alg(J.alg, &S, J.R, J.c, &kernel);
+    if (!d) { std::lock_guard<std::mutex> lk(J.mu); J.error = "unknown algorithm " + J.alg; return; }
+    Distributed_ALS als(d, false);
+    DenseMatrix Agt = d->like_A_matrix(0.0), Bgt = d->like_B_matrix(0.0);
+    gather_local(Agt, d->aSubmatrices, G.Agt, J.M, J.R);
+    gather_local(Bgt, d->bSubmatrices, G.Bgt, J.N, J.R);
+    VectorXd ones = d->like_S_values(1.0);
+    als.ground_truth = d->like_S_values(0.0);
+    d->initial_shift(&Agt, &Bgt, k_sddmmA);
+    d->sddmmA(Agt, Bgt, ones, als.ground_truth);
+    d->de_shift(&Agt, &Bgt, k_sddmmA);
+    ones = d->like_ST_values(1.0);
+    als.ground_truth_transpose = d->like_ST_values(0.0);
+    d->initial_shift(&Agt, &Bgt, k_sddmmB);
+    d->sddmmB(Agt, Bgt, ones, als.ground_truth_transpose);
+    d->de_shift(&Agt, &Bgt, k_sddmmB);
+    als.A = d->like_A_matrix(0.0);
+    als.B = d->like_B_matrix(0.0);
+    gather_local(als.A, d->aSubmatrices, G.A0, J.M, J.R);
+    gather_local(als.B, d->bSubmatrices, G.B0, J.N, J.R);
+    const double before = als.computeResidual();
+    for (int i = 0; i < G.steps; i++) {
+        als.cg_optimizer(Amat, G.cg_iters);
+        als.cg_optimizer(Bmat, G.cg_iters);
+    }
+    const double after = als.computeResidual();
+    if (rank == 0) { G.residual[0] = before; G.residual[1] = after; }
+    G.A_out[(size_t)rank] = flatten(als.A);
+    G.B_out[(size_t)rank] = flatten(als.B);
+    std::vector<int> &sh = G.shape[(size_t)rank];
+    sh = {d->localArows, d->localAcols, d->localBrows, d->localBcols, (int)d->aSubmatrices.size(), (int)d->bSubmatrices.size()};
+    for (auto &s : d->aSubmatrices) { sh.push_back(s.topRow); sh.push_back(s.leftCol); sh.push_back(s.rowCount); sh.push_back(s.colCount); }
+    for (auto &s : d->bSubmatrices) { sh.push_back(s.topRow); sh.push_back(s.leftCol); sh.push_back(s.rowCount); sh.push_back(s.colCount); }
+    delete d;
+}
+struct ref_als_result { Job job; AlsArgs args; };
+ref_als_result *ref_als(const char *alg, int p, int c, int R, int64_t M, int64_t N, int64_t nnz, const uint64_t *rows,
+                        const uint64_t *cols, const double *vals, const double *Agt, const double *Bgt, const double *A0,
+                        const double *B0, int steps, int cg_iters, int threads_per_rank) {
+    ref_als_result *r = new ref_als_result();
+    Job &J = r->job;
+    J.alg = alg; J.p = p; J.c = c; J.R = R; J.M = M; J.N = N; J.nnz = nnz; J.rows = rows; J.cols = cols; J.vals = vals;
+    J.A = nullptr; J.B = nullptr;
+    AlsArgs &G = r->args;
+    G.job = &J; G.Agt = Agt; G.Bgt = Bgt; G.A0 = A0; G.B0 = B0; G.steps = steps; G.cg_iters = cg_iters;
+    G.A_out.resize((size_t)p); G.B_out.resize((size_t)p); G.shape.resize((size_t)p);
+    G.residual[0] = G.residual[1] = 0.0;
+    hmpi_run(p, threads_per_rank, als_main, &G);
+    return r;
+}
+const char *ref_als_error(ref_als_result *r) { return r->job.error.c_str(); }
+void ref_als_residuals(ref_als_result *r, double *out2) { out2[0] = r->args.residual[0]; out2[1] = r->args.residual[1]; }
+int ref_als_shape_len(ref_als_result *r, int rank) { return (int)r->args.shape[(size_t)rank].size(); }
+const int *ref_als_shape(ref_als_result *r, int rank) { return r->args.shape[(size_t)rank].data(); }
+const double *ref_als_A(ref_als_result *r, int rank) { return r->args.A_out[(size_t)rank].data(); }
+const double *ref_als_B(ref_als_result *r, int rank) { return r->args.B_out[(size_t)rank].data(); }
+void ref_als_free(ref_als_result *r) { delete r; }
 
 }  // extern "C"

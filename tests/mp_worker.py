@@ -35,6 +35,14 @@ def gat_inputs(N, layers, seed):
     return layers, X0, weights
 
 
+def als_inputs(N, R, seed):
+    """Deterministic ALS test inputs (global): ground-truth factors and starting embeddings."""
+    rng = np.random.default_rng(seed + 99)
+    Agt, Bgt = rng.uniform(-1, 1, (N, R)) / R, rng.uniform(-1, 1, (N, R)) / R
+    A0, B0 = 1.4 * rng.uniform(-1, 1, (N, R)) / R, rng.uniform(-1, 1, (N, R)) / R / 1.3
+    return Agt, Bgt, A0, B0
+
+
 def gather_local(G, subs, shape):
     out = np.zeros(shape)
     flat = out.reshape(-1)
@@ -164,6 +172,14 @@ def main():
                 alg.fusedSpMM_host(A, B, Sv, res, hA, hB, got, mode, chunk_rows=case["hostpipe"])
                 out[f"hostpipe_{mode}_got"] = got
                 out[f"hostpipe_{mode}_staged"] = (A if mode == "A" else B).to_host()
+        if have_gpu and case.get("als_parity"):
+            # Distributed_ALS on given inputs (hnhd_als_run), to be compared with the reference's own ALS run
+            shapeA, shapeB = (d.localArows, d.localAcols), (d.localBrows, d.localBcols)
+            subsA, subsB = alg.submatrices("A"), alg.submatrices("B")
+            Agt, Bgt, A0, B0 = als_inputs(N, R, seed)
+            res, locA, locB = D.als_run(alg, gather_local(Agt, subsA, shapeA), gather_local(Bgt, subsB, shapeB),
+                                        gather_local(A0, subsA, shapeA), gather_local(B0, subsB, shapeB), 1, 10)
+            out["als_res"], out["als_A"], out["als_B"] = np.array(res), locA, locB
         if have_gpu and case.get("gat"):
             # GAT forward pass on this algorithm object (dense-shift layouts: one row block per rank, full width)
             g = case["gat"]

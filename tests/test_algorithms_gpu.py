@@ -230,3 +230,24 @@ def test_p1_gat_forward_matches_global_model(world, name):
     assert (want != 0).mean() > 0.2
     assert rel_err(net.buffer(2), want) < RTOL
     assert rel_err(net.buffer(1), orc.gat_forward_global(rows, cols, N, layers[:1], weights[:1], 0.2, X0)) < RTOL
+
+
+@unvalidated
+@pytest.mark.parametrize("name", ALGS)
+def test_p1_als_cg_matches_reference_als(world, name):
+    """One alternating round of batched CG on given inputs against the reference's own Distributed_ALS (oracle/_ref)."""
+    from oracle import ref
+    from tests.mp_worker import als_inputs
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built")
+    logM, npr, R = 8, 6, 16
+    N = 1 << logM
+    rows, cols, _ = orc.er_tuples(logM, npr, SEED)
+    Agt, Bgt, A0, B0 = als_inputs(N, R, SEED)
+    S = D.SpmatLocal.load_er(logM, npr, SEED)
+    alg = D.Algorithm(name, S, R, 1)
+    res, A, B = D.als_run(alg, Agt, Bgt, A0, B0, 1, 10)
+    want = ref.als(name, 1, 1, R, N, rows, cols, Agt, Bgt, A0, B0, 1, 10)
+    assert res[1] < 0.5 * res[0]
+    assert np.allclose(res, want["residual"], rtol=1e-7, atol=0)
+    assert rel_err(A, want["A"]) < 1e-7 and rel_err(B, want["B"]) < 1e-7

@@ -124,3 +124,40 @@ def test_fused_host_operands_multirank(nproc):
                 want = rank_out[f"hostpipe_{mode}_want"]
                 assert np.array_equal(rank_out[f"hostpipe_{mode}_got"], want), (c["name"], r, mode)
                 assert np.array_equal(rank_out[f"hostpipe_{mode}_staged"], want), (c["name"], r, mode)
+
+
+ALS_CASES = {
+    2: [dict(U.case("15d_fusion1", 1, 8, 7, 5, script=[], name="alsp_fusion1_c1"), als_parity=1),
+        dict(U.case("15d_fusion2", 2, 8, 7, 5, script=[], name="alsp_fusion2_c2"), als_parity=1),
+        dict(U.case("15d_sparse", 1, 8, 7, 5, script=[], name="alsp_sparse_c1"), als_parity=1)],
+    4: [dict(U.case("15d_fusion2", 1, 8, 7, 5, script=[], name="alsp_fusion2_c1"), als_parity=1),
+        dict(U.case("15d_sparse", 2, 8, 7, 5, script=[], name="alsp_sparse_c2"), als_parity=1),
+        dict(U.case("25d_dense_replicate", 1, 8, 7, 5, script=[], name="alsp_25d_dense"), als_parity=1),
+        dict(U.case("25d_sparse_replicate", 1, 8, 7, 5, script=[], name="alsp_25d_sparse"), als_parity=1)],
+}
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_als_cg_matches_reference_als(nproc):
+    """BASELINE.json config 5's caller: one alternating round of batched CG (10 iterations per side) on given ground
+    truth and starting embeddings, against the reference's own Distributed_ALS / cg_optimizer run by oracle/_ref --
+    residuals and every rank's local embeddings.  Tolerance 1e-7 relative (contract 1e-5): 20 CG iterations separate
+    the two summation orders."""
+    from oracle import hnh_oracle as orc
+    from oracle import ref
+    from tests.mp_worker import als_inputs
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built")
+    cases = ALS_CASES[nproc]
+    got = U.run_cases(nproc, cases, transport_for(nproc), timeout=900)
+    for c in cases:
+        N = 1 << c["logM"]
+        rows, cols, _ = orc.er_tuples(c["logM"], c["npr"], c["seed"])
+        want = ref.als(c["alg"], nproc, c["c"], c["R"], N, rows, cols, *als_inputs(N, c["R"], c["seed"]), 1, 10)
+        for r, (wA, wB) in enumerate(want["ranks"]):
+            g = got[c["name"]][r]
+            assert np.allclose(g["als_res"], want["residual"], rtol=1e-7, atol=0), (c["name"], r, g["als_res"], want["residual"])
+            for have, w in ((g["als_A"], wA), (g["als_B"], wB)):
+                assert have.shape == w.shape, (c["name"], r)
+                assert np.abs(have - w).max() <= 1e-7 * np.abs(w).max(), (c["name"], r)
