@@ -79,6 +79,23 @@ def fusedmm_bytes_per_rank(alg: str, nnz_rank: float, rows_stationary: int, step
     return sddmm + spmm + 5 * w * nnz_rank
 
 
+NVLINK_GBS_NOMINAL = 900.0  # NVLink 5, per GPU and direction (B200_PROFILING.md); MEASURED_PEAKS.json has no link figure
+
+
+def nvlink_bytes_per_rank(alg: str, p: int, c: int, local_rows: int, r: int) -> float:
+    """Bytes one rank RECEIVES over NVLink in one FusedMM of the 1.5D dense-shift algorithm:
+    every ring pass delivers p/c - 1 riding shards of local_rows x r doubles; replication (c > 1) adds the
+    all-gather of the stationary operand (c - 1 shards in) and, for local kernel fusion, the reduce-scatter of
+    the c x larger accumulator (c - 1 shard-sized partial sums in).  Fusion 2 makes one ring pass per FusedMM,
+    fusion 1 (replication reuse: SDDMM pass + SpMM pass, gathered operand reused) makes two."""
+    shard = 8.0 * local_rows * r
+    ring = (p // c - 1) * shard
+    gather = (c - 1) * shard
+    if alg == "15d_fusion2":
+        return ring + 2 * gather
+    return 2 * ring + gather + gather  # fusion 1: the SpMM pass reduce-scatters its replicated output too
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (NVML, 5 ms period)."""
 
@@ -364,6 +381,15 @@ def run_native(args):
         g, cores, kind, desc, _ = cpu_reference_fusedmm(args, 1, 3)
         cpu = {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc}
 
+    nvlink = None
+    if world > 1:
+        try:  # explanatory only: never let it cost the line
+            nb = nvlink_bytes_per_rank(args.alg, world, c, alg.dims.localBrows, R)
+            nvlink = {"bytes_in_per_gpu_per_step": nb, "peak_gbs": NVLINK_GBS_NOMINAL, "peak_kind": "nominal",
+                      "bound_ms": nb / (NVLINK_GBS_NOMINAL * 1e9) * 1e3, "achieved_gbs": nb / (ms * 1e-3) / 1e9}
+        except Exception:  # noqa: BLE001
+            nvlink = None
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -378,6 +404,8 @@ def run_native(args):
         }
         if other:
             line["other"] = other
+        if nvlink:
+            line["nvlink"] = nvlink
         print(json.dumps(line))
     del alg, S
     D.world_finalize()
