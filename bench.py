@@ -86,14 +86,15 @@ def nvlink_bytes_per_rank(alg: str, p: int, c: int, local_rows: int, r: int) -> 
     """Bytes one rank RECEIVES over NVLink in one FusedMM of the 1.5D dense-shift algorithm:
     every ring pass delivers p/c - 1 riding shards of local_rows x r doubles; replication (c > 1) adds the
     all-gather of the stationary operand (c - 1 shards in) and, for local kernel fusion, the reduce-scatter of
-    the c x larger accumulator (c - 1 shard-sized partial sums in).  Fusion 2 makes one ring pass per FusedMM,
-    fusion 1 (replication reuse: SDDMM pass + SpMM pass, gathered operand reused) makes two."""
+    the c x larger accumulator (c - 1 shard-sized partial sums in).  Fusion 2 makes one ring pass per FusedMM.
+    Fusion 1 (replication reuse) makes two -- the SDDMM pass, and the SpMM pass in which the OUTPUT rides and
+    therefore goes all the way round (p/c shifts) -- gathers once and never reduce-scatters."""
     shard = 8.0 * local_rows * r
-    ring = (p // c - 1) * shard
+    steps = p // c
     gather = (c - 1) * shard
     if alg == "15d_fusion2":
-        return ring + 2 * gather
-    return 2 * ring + gather + gather  # fusion 1: the SpMM pass reduce-scatters its replicated output too
+        return (steps - 1) * shard + 2 * gather
+    return ((steps - 1) + (steps if steps > 1 else 0)) * shard + gather
 
 
 class ClockSampler:
