@@ -11,3 +11,5 @@ LOGM=22 NPR=64 R=32 ALGS=15d_sparse CS=1,8 timeout 300 $T scripts/scale_sweep.py
 LOGM=20 NPR=32 R=256 ALGS=25d_dense_replicate,25d_sparse_replicate CS=2 timeout 300 $T scripts/scale_sweep.py > gpurun_out/r2_sweep8_cfg4.log 2>&1; grep '^{' gpurun_out/r2_sweep8_cfg4.log | cut -c1-400
 timeout 300 $T bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench8.json 2> gpurun_out/r2_bench8.err; tail -c 800 gpurun_out/r2_bench8.json
 timeout 300 $T bench.py --gpus 8 --steps 10 --warmup 3 --e2e-pipeline > gpurun_out/r2_bench8_pipe.json 2> gpurun_out/r2_bench8_pipe.err; tail -c 500 gpurun_out/r2_bench8_pipe.json
+# BASELINE config 5: FusedMM stand-alone and inside one ALS-CG round, N = 2^21, r = 128, 8 GPUs (and the GAT pass for the record)
+LOGM=21 NPR=32 R=128 APPS=vanilla,als timeout 600 $T scripts/app_bench.py > gpurun_out/r2_cfg5_apps.log 2>&1; grep '^{' gpurun_out/r2_cfg5_apps.log | cut -c1-600
