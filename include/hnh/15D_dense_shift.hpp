@@ -164,7 +164,8 @@ public:
         DenseMatrix &gathered = c > 1 ? broadcast_buffer : *stationary;
         // With one ring step and no replication the output row i depends only on input row i:
         // the fused kernel may then write the result over its own input.
-        const bool in_place = sk && steps == 1 && c == 1;
+        // (the in-place kernels exist for the widths of the dispatch table only: 4..256, powers of two)
+        const bool in_place = sk && steps == 1 && c == 1 && in_place_width(gathered.cols());
         if (!in_place) accumulation_buffer.resize(gathered.rows(), gathered.cols());
         DenseMatrix &out = in_place ? *stationary : accumulation_buffer;
         if (!sk) {
@@ -198,7 +199,8 @@ public:
     void fusedSpMM_host(const double *hostA, const double *hostB, double *hostOut, DenseMatrix &localA,
                         DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer, MatMode mode) override {
         StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
-        if (fusionApproach != 2 || c != 1 || sk == nullptr || host_pipeline_chunk_rows <= 0) {
+        const int64_t width = (mode == Amat ? localA : localB).cols();
+        if (fusionApproach != 2 || c != 1 || sk == nullptr || host_pipeline_chunk_rows <= 0 || (p == 1 && !in_place_width(width))) {
             Distributed_Sparse::fusedSpMM_host(hostA, hostB, hostOut, localA, localB, Svalues, sddmm_buffer, mode);
             return;
         }
@@ -239,6 +241,8 @@ public:
     }
 
 private:
+    static bool in_place_width(int64_t r) { return r >= 4 && r <= 256 && (r & (r - 1)) == 0; }
+
     // p > 1, c = 1: see fusedSpMM_host.  Block b of this rank's block row multiplies the shard owned by rank b of
     // the column communicator (block_at(step) with c = 1 is (rankInCol - step) mod p, the owner of the shard the
     // ring would deliver at that step), so the all-gathered riding operand is indexed by block id.

@@ -251,3 +251,32 @@ def test_p1_als_cg_matches_reference_als(world, name):
     assert res[1] < 0.5 * res[0]
     assert np.allclose(res, want["residual"], rtol=1e-7, atol=0)
     assert rel_err(A, want["A"]) < 1e-7 and rel_err(B, want["B"]) < 1e-7
+
+
+@unvalidated
+@pytest.mark.parametrize("R", [12, 192])
+def test_p1_fusion2_fused_widths_outside_the_dispatch_table(world, R):
+    """fusedSpMM of the local-kernel-fusion algorithm on one rank at a width without an in-place kernel (the
+    reference's bench_heatmap.cpp sweeps R = 64 ... 448 in steps of 64): falls back to the accumulate-into-a-buffer
+    path with the generic kernel."""
+    logM, npr = 9, 6
+    N = 1 << logM
+    rows, cols, _ = orc.er_tuples(logM, npr, SEED)
+    rng = np.random.default_rng(R)
+    A0, B0 = rng.uniform(-1, 1, (N, R)), rng.uniform(-1, 1, (N, R))
+    S = D.SpmatLocal.load_er(logM, npr, SEED)
+    alg = D.Algorithm("15d_fusion2", S, R, 1)
+    A, B = alg.like_A_matrix(), alg.like_B_matrix()
+    Sv, res = alg.like_S_values(1.0), alg.like_S_values(0.0)
+    for mode in ("A", "B"):
+        A.from_host(A0)
+        B.from_host(B0)
+        if mode == "B":
+            Sv, res = alg.like_ST_values(1.0), alg.like_ST_values(0.0)
+        alg.fusedSpMM(A, B, Sv, res, mode)
+        if mode == "A":
+            _, _, _, _, want = orc.global_reference(rows, cols, np.ones(len(rows)), A0, B0)
+            assert rel_err(A.to_host(), want) < RTOL
+        else:
+            _, _, _, _, want = orc.global_reference(cols, rows, np.ones(len(rows)), B0, A0)  # S^T in the role of S
+            assert rel_err(B.to_host(), want) < RTOL
