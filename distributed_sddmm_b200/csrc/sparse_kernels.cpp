@@ -56,6 +56,8 @@ void StandardKernel::fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix
         return;
     }
     if (blk->transpose) throw hnh::Error(HNH_E_MODE, "fused_local_rows needs a non-transposed block");
+    if (r < 4 || r > 256 || (r & (r - 1)) != 0)  // the generic kernel's overwrite mode clears the whole block's values
+        throw hnh::Error(HNH_E_INVALID, "fused_local_rows: width outside the dispatch table");
     if (row0 < 0 || row0 + nrows > blk->rows) throw hnh::Error(HNH_E_INVALID, "fused_local_rows: row range");
     CSRHandle *h = blk->getActive();
     // rowStart entries are absolute offsets into col_idx / values, so a row range is the same call on shifted

@@ -200,7 +200,9 @@ public:
                         DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer, MatMode mode) override {
         StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
         const int64_t width = (mode == Amat ? localA : localB).cols();
-        if (fusionApproach != 2 || c != 1 || sk == nullptr || host_pipeline_chunk_rows <= 0 || (p == 1 && !in_place_width(width))) {
+        // (row-range launches need a table width: the generic kernel's overwrite mode clears the values of the
+        // whole block, not of a row range)
+        if (fusionApproach != 2 || c != 1 || sk == nullptr || host_pipeline_chunk_rows <= 0 || !in_place_width(width)) {
             Distributed_Sparse::fusedSpMM_host(hostA, hostB, hostOut, localA, localB, Svalues, sddmm_buffer, mode);
             return;
         }

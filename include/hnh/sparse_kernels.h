@@ -71,7 +71,8 @@ public:
                        bool out_is_zero) override;
     // fused_local restricted to the CSR rows [row0, row0 + nrows) of the block: the unit of the host-operand
     // pipeline (fusedSpMM_host).  The block's values of those rows are overwritten (first visit); the rows of
-    // Out are overwritten when out_is_zero (Out may then be X), accumulated into otherwise.
+    // Out are overwritten when out_is_zero (Out may then be X), accumulated into otherwise.  Only for the widths
+    // of the dispatch table (4..256, powers of two); throws otherwise.
     void fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block, int64_t row0,
                           int64_t nrows, bool out_is_zero = true);
 };
