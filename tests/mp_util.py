@@ -41,11 +41,13 @@ def run_cases(nproc, cases, transport, timeout=600):
         return out
 
 
-def case(alg, c, R, logM, npr, seed=0xC0FFEE + 1, script=ALL_OPS, name=None, load="tuples", n=None):
-    d = dict(name=name or f"{alg}_c{c}_R{R}_m{logM}" + (f"_n{n}" if n else ""), alg=alg, c=c, R=R, logM=logM, npr=npr,
-             seed=seed, script=list(script), load=load)
+def case(alg, c, R, logM, npr, seed=0xC0FFEE + 1, script=ALL_OPS, name=None, load="tuples", n=None, m=None):
+    d = dict(name=name or f"{alg}_c{c}_R{R}_m{logM}" + (f"_n{n}" if n else "") + (f"_rows{m}" if m else ""), alg=alg, c=c, R=R,
+             logM=logM, npr=npr, seed=seed, script=list(script), load=load)
     if n:
         d["n"] = n
+    if m:
+        d["m"] = m  # rectangular: m rows, n (or 2^logM) columns
     return d
 
 
@@ -55,14 +57,15 @@ def reference_for(case_, p):
     from oracle import ref
     from tests.mp_worker import global_inputs, sval
     N = case_.get("n") or (1 << case_["logM"])
-    rows, cols, _ = orc.er_tuples(case_["logM"], case_["npr"], case_["seed"], 0, N)
+    M = case_.get("m") or N
+    rows, cols, _ = orc.er_tuples(case_["logM"], case_["npr"], case_["seed"], 0, M)
     keep = cols < N
     rows, cols = rows[keep], cols[keep]
-    A, B = global_inputs(N, case_["R"], case_["seed"])
+    A, B = global_inputs(N, case_["R"], case_["seed"], M)
     golden = os.path.join(ROOT, "tests", "golden", f"{case_['name']}_p{p}.npz")
     if ref.available():
         vals = np.ones(len(rows)) if case_.get("load") == "er" else sval(rows, cols)
-        ranks = ref.run(case_["alg"], p, case_["c"], case_["R"], N, N, rows, cols, vals, A, B, case_["script"])
+        ranks = ref.run(case_["alg"], p, case_["c"], case_["R"], M, N, rows, cols, vals, A, B, case_["script"])
         return ranks, "oracle/_ref"
     if os.path.exists(golden):
         return load_golden(golden, p), "tests/golden"

@@ -21,9 +21,14 @@ def sval(r, c):
     return 0.5 + ((r.astype(np.int64) * 31 + c.astype(np.int64) * 17) % 97) / 97.0
 
 
-def global_inputs(N, R, seed):
+def global_inputs(N, R, seed, M=None):
+    """A (M x R) and B (N x R); M defaults to N.  The draws for B do not depend on M."""
     rng = np.random.default_rng(seed)
-    return rng.uniform(-1, 1, (N, R)), rng.uniform(-1, 1, (N, R))
+    A = rng.uniform(-1, 1, (N, R))
+    B = rng.uniform(-1, 1, (N, R))
+    if M is not None and M != N:
+        A = np.random.default_rng(seed + 1).uniform(-1, 1, (M, R))
+    return A, B
 
 
 def gat_inputs(N, layers, seed):
@@ -71,18 +76,19 @@ def main():
     for case in cases:
         name, alg_name, c, R, logM, npr, seed, script = (case[k] for k in ("name", "alg", "c", "R", "logM", "npr", "seed", "script"))
         N = case.get("n") or (1 << logM)  # "n": a size that does not divide evenly among the ranks
+        M = case.get("m") or N            # "m": a rectangular M x N matrix (rows of the generator below M)
         if case.get("load", "tuples") == "er":
             # SpmatLocal::loadTuples(false, logM, npr, ""): every rank generates its row slice, values 1.0
             S = D.SpmatLocal.load_er(logM, npr, seed)
         else:
             # caller-provided tuples with coordinate-dependent values, dealt to the ranks in contiguous slices
             from oracle import hnh_oracle as orc
-            per = N // world
-            lo, hi = per * rank, (N if rank == world - 1 else per * (rank + 1))
+            per = M // world
+            lo, hi = per * rank, (M if rank == world - 1 else per * (rank + 1))
             tr, tc, _ = orc.er_tuples(logM, npr, seed, lo, hi)
             keep = tc < N
             tr, tc = tr[keep], tc[keep]
-            S = D.SpmatLocal.from_tuples(N, N, tr, tc, sval(tr, tc))
+            S = D.SpmatLocal.from_tuples(M, N, tr, tc, sval(tr, tc))
         alg = D.Algorithm(alg_name, S, R, c)
         d = alg.dims
         out = dict(i=d.grid_i, j=d.grid_j, k=d.grid_k, localArows=d.localArows, localAcols=d.localAcols,
@@ -98,7 +104,7 @@ def main():
                         out[f"{key}_b{b}_{f}"] = blk[f]
         if have_gpu and script:
             A, B = alg.like_A_matrix(), alg.like_B_matrix()
-            GA, GB = global_inputs(N, R, seed)  # same N as the reference side
+            GA, GB = global_inputs(N, R, seed, M)  # same sizes as the reference side
             shapeA, shapeB = (d.localArows, d.localAcols), (d.localBrows, d.localBcols)
             subsA, subsB = alg.submatrices("A"), alg.submatrices("B")
 

@@ -17,6 +17,9 @@ CASES_2 = [
     # sizes that do not divide evenly: trailing blocks are padded (ceil-div sizing, common.cpp:20-27)
     U.case("15d_fusion2", 1, 8, 7, 5, n=101),
     U.case("15d_sparse", 1, 8, 7, 5, n=101),
+    # rectangular matrices (more columns than rows and the reverse; neither divides evenly)
+    U.case("15d_fusion2", 1, 8, 7, 5, n=120, m=75, name="nogolden_rect_fusion2"),
+    U.case("15d_sparse", 2, 8, 7, 5, n=70, m=128, name="nogolden_rect_sparse"),
     # 650k tuples: the multi-threaded bucketing / counting-sort paths of the setup (needs oracle/_ref; no golden file)
     U.case("15d_fusion1", 1, 8, 14, 40, name="nogolden_big_fusion1"),
     U.case("25d_sparse_replicate", 2, 8, 14, 40, name="nogolden_big_25d_sparse"),
@@ -28,6 +31,9 @@ CASES_4 = [
     U.case("25d_sparse_replicate", 1, 8, 7, 5),
     U.case("15d_fusion1", 2, 8, 7, 5, n=99),
     U.case("25d_dense_replicate", 1, 8, 7, 5, n=99),
+    U.case("15d_fusion1", 1, 8, 7, 5, n=100, m=61, name="nogolden_rect_fusion1"),
+    U.case("25d_dense_replicate", 1, 8, 7, 5, n=90, m=128, name="nogolden_rect_25d_dense"),
+    U.case("25d_sparse_replicate", 1, 8, 7, 5, n=128, m=77, name="nogolden_rect_25d_sparse"),
 ]
 # the grid shapes of the 8-GPU runs (BASELINE.json configs 2-5): p=8 with c = 1, 2, 4, 8; 2.5D with s=2, c=2
 CASES_8 = [

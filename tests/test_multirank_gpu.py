@@ -161,3 +161,34 @@ def test_als_cg_matches_reference_als(nproc):
             for have, w in ((g["als_A"], wA), (g["als_B"], wB)):
                 assert have.shape == w.shape, (c["name"], r)
                 assert np.abs(have - w).max() <= 1e-7 * np.abs(w).max(), (c["name"], r)
+
+
+RECT_CASES = {
+    2: [U.case("15d_fusion2", 1, 8, 7, 5, n=120, m=75, name="nogolden_rect_fusion2"),
+        U.case("15d_fusion1", 2, 8, 7, 5, n=70, m=128, name="nogolden_rect_fusion1"),
+        U.case("15d_sparse", 2, 8, 7, 5, n=70, m=128, name="nogolden_rect_sparse")],
+    4: [U.case("15d_fusion1", 1, 8, 7, 5, n=100, m=61, name="nogolden_rect_fusion1"),
+        U.case("15d_fusion2", 2, 8, 7, 5, n=128, m=77, name="nogolden_rect_fusion2"),
+        U.case("15d_sparse", 1, 8, 7, 5, n=100, m=61, name="nogolden_rect_sparse"),
+        U.case("25d_dense_replicate", 1, 8, 7, 5, n=90, m=128, name="nogolden_rect_25d_dense"),
+        U.case("25d_sparse_replicate", 1, 8, 7, 5, n=128, m=77, name="nogolden_rect_25d_sparse")],
+}
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_rectangular_matrices_match_reference(nproc):
+    """M != N (more columns than rows and the reverse, sizes that do not divide evenly): every public operation of
+    every algorithm against the reference's own code, as in test_all_operations_match_reference."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built")
+    cases = RECT_CASES[nproc]
+    got = U.run_cases(nproc, cases, transport_for(nproc), timeout=900)
+    for c in cases:
+        want, src = U.reference_for(c, nproc)
+        try:
+            U.compare_layout(got[c["name"]], want, c["alg"])
+            U.compare_ops(got[c["name"]], want, c["script"])
+        except AssertionError as e:
+            raise AssertionError(f"case {c['name']} (p={nproc}, reference from {src}): {e}") from e
