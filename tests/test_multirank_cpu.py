@@ -31,6 +31,12 @@ CASES_4 = [
     U.case("25d_sparse_replicate", 1, 8, 7, 5),
     U.case("15d_fusion1", 2, 8, 7, 5, n=99),
     U.case("25d_dense_replicate", 1, 8, 7, 5, n=99),
+    # 16 x 16 with one nonzero per row on 4 ranks: null blocks and empty CSR blocks
+    U.case("15d_fusion1", 1, 4, 4, 1, name="nogolden_tiny_fusion1"),
+    U.case("15d_fusion2", 2, 4, 4, 1, name="nogolden_tiny_fusion2"),
+    U.case("15d_sparse", 4, 4, 4, 1, name="nogolden_tiny_sparse"),
+    U.case("25d_dense_replicate", 1, 4, 4, 1, name="nogolden_tiny_25d_dense"),
+    U.case("25d_sparse_replicate", 1, 4, 4, 1, name="nogolden_tiny_25d_sparse"),
     U.case("15d_fusion1", 1, 8, 7, 5, n=100, m=61, name="nogolden_rect_fusion1"),
     U.case("25d_dense_replicate", 1, 8, 7, 5, n=90, m=128, name="nogolden_rect_25d_dense"),
     U.case("25d_sparse_replicate", 1, 8, 7, 5, n=128, m=77, name="nogolden_rect_25d_sparse"),

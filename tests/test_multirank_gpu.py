@@ -192,3 +192,27 @@ def test_rectangular_matrices_match_reference(nproc):
             U.compare_ops(got[c["name"]], want, c["script"])
         except AssertionError as e:
             raise AssertionError(f"case {c['name']} (p={nproc}, reference from {src}): {e}") from e
+
+
+TINY_CASES = [U.case("15d_fusion1", 1, 4, 4, 1, name="nogolden_tiny_fusion1"), U.case("15d_fusion2", 2, 4, 4, 1, name="nogolden_tiny_fusion2"),
+              U.case("15d_fusion2", 1, 4, 4, 1, name="nogolden_tiny_fusion2_c1"), U.case("15d_sparse", 4, 4, 4, 1, name="nogolden_tiny_sparse"),
+              U.case("15d_sparse", 1, 4, 4, 1, name="nogolden_tiny_sparse_c1"),
+              U.case("25d_dense_replicate", 1, 4, 4, 1, name="nogolden_tiny_25d_dense"),
+              U.case("25d_sparse_replicate", 1, 4, 4, 1, name="nogolden_tiny_25d_sparse")]
+
+
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+def test_null_and_empty_blocks_match_reference():
+    """A 16 x 16 matrix with one nonzero per row on 4 ranks: most blocks are null or empty (the reference skips them,
+    sparse_kernels.cpp:25-27,71-73,85-87); every operation must still agree with it."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref is not built")
+    got = U.run_cases(4, TINY_CASES, transport_for(4), timeout=900)
+    for c in TINY_CASES:
+        want, src = U.reference_for(c, 4)
+        try:
+            U.compare_layout(got[c["name"]], want, c["alg"])
+            U.compare_ops(got[c["name"]], want, c["script"])
+        except AssertionError as e:
+            raise AssertionError(f"case {c['name']} (reference from {src}): {e}") from e
