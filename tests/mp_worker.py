@@ -83,9 +83,18 @@ def main():
         else:
             # caller-provided tuples with coordinate-dependent values, dealt to the ranks in contiguous slices
             from oracle import hnh_oracle as orc
-            per = M // world
-            lo, hi = per * rank, (M if rank == world - 1 else per * (rank + 1))
-            tr, tc, _ = orc.er_tuples(logM, npr, seed, lo, hi)
+            deal = case.get("deal", "slices")
+            if deal == "slices":      # contiguous row slices
+                per = M // world
+                lo, hi = per * rank, (M if rank == world - 1 else per * (rank + 1))
+                tr, tc, _ = orc.er_tuples(logM, npr, seed, lo, hi)
+            else:
+                tr, tc, _ = orc.er_tuples(logM, npr, seed, 0, M)
+                if deal == "last":    # everything starts on the last rank
+                    mine = np.full(len(tr), rank == world - 1)
+                else:                 # "scatter": rows dealt round-robin-ish, handed over in reverse order
+                    mine = (tr.astype(np.int64) * 7 + 3) % world == rank
+                tr, tc = tr[mine][::-1].copy(), tc[mine][::-1].copy()
             keep = tc < N
             tr, tc = tr[keep], tc[keep]
             S = D.SpmatLocal.from_tuples(M, N, tr, tc, sval(tr, tc))

@@ -31,6 +31,9 @@ CASES_4 = [
     U.case("25d_sparse_replicate", 1, 8, 7, 5),
     U.case("15d_fusion1", 2, 8, 7, 5, n=99),
     U.case("25d_dense_replicate", 1, 8, 7, 5, n=99),
+    # any initial distribution of the tuples is legal input: all on the last rank / scattered and handed over unsorted
+    dict(U.case("15d_fusion2", 2, 8, 7, 5, n=101, m=90, name="nogolden_deal_last"), deal="last"),
+    dict(U.case("15d_sparse", 1, 8, 7, 5, n=101, m=90, name="nogolden_deal_scatter"), deal="scatter"),
     # 16 x 16 with one nonzero per row on 4 ranks: null blocks and empty CSR blocks
     U.case("15d_fusion1", 1, 4, 4, 1, name="nogolden_tiny_fusion1"),
     U.case("15d_fusion2", 2, 4, 4, 1, name="nogolden_tiny_fusion2"),
