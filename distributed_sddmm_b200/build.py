@@ -88,18 +88,30 @@ def build_reference_driver() -> str | None:
                 _compile_reference_main(path, name)
             except subprocess.CalledProcessError as e:  # the headline driver above is the required one
                 sys.stderr.write(f"build: {other} did not compile against include/hnh/compat ({e})\n")
+    # the reference's benchmark HARNESS as well: bench_erdos_renyi.cpp + its own benchmark_dist.cpp (benchmark_algorithm:
+    # algorithm selection, inputs, trial loop, FLOP model, JSON record), both unchanged, on this library's classes.  The
+    # executable's benchmark_algorithm takes precedence over the library's.
+    try:
+        _compile_reference_main(src, "bench_er_reference_harness", extra=["/root/reference/benchmark_dist.cpp"])
+    except subprocess.CalledProcessError as e:
+        sys.stderr.write(f"build: the reference's benchmark_dist.cpp did not compile against include/hnh/compat ({e})\n")
     return exe
 
 
-def _compile_reference_main(src: str, name: str) -> str:
+def _compile_reference_main(src: str, name: str, extra: list[str] | None = None) -> str:
     exe = os.path.join(HERE, name)
-    obj = os.path.join(HERE, "build", name + ".o")
-    os.makedirs(os.path.dirname(obj), exist_ok=True)
-    with open(src, "rb") as f:
-        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-x", "c++", "-c", "-o", obj,
-                               "-I" + os.path.join(ROOT, "include", "hnh", "compat"), "-I" + os.path.join(ROOT, "include"),
-                               "-I/usr/local/cuda/include", "-"], stdin=f, cwd="/tmp")
-    subprocess.check_call(["/usr/bin/g++", "-o", exe, obj, "-L" + HERE, "-lhnh_b200", "-Wl,-rpath,$ORIGIN"])
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objs = []
+    for i, path in enumerate([src] + list(extra or [])):
+        obj = os.path.join(HERE, "build", f"{name}.{i}.o")
+        with open(path, "rb") as f:  # through stdin: the source's directory must not shadow the compat headers
+            subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-x", "c++", "-c", "-o", obj,
+                                   "-I" + os.path.join(ROOT, "include", "hnh", "compat"), "-I" + os.path.join(ROOT, "include"),
+                                   "-I/usr/local/cuda/include", "-"], stdin=f, cwd="/tmp")
+        objs.append(obj)
+    # sources that instantiate the algorithm classes (header-inline code) call the CUDA runtime directly
+    cudart = ["-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread"] if extra else []
+    subprocess.check_call(["/usr/bin/g++", "-o", exe, *objs, "-L" + HERE, "-lhnh_b200", "-Wl,-rpath,$ORIGIN", *cudart])
     return exe
 
 

@@ -2,7 +2,7 @@
 # 1. the paths written at the end of round 1 without GPU time (gated tests), 2. the full GPU suite,
 # 3. the bench line with and without the pipelined host-operand e2e leg, 4. per-warp TMA vs the defaults.
 mkdir -p gpurun_out
-HNH_UNVALIDATED=1 timeout 900 python -m pytest tests -q -rfE -m gpu -k "als_cg_matches or null_and_empty or rectangular or dispatch_table or host_operands or hostpipe or gat or device_ or file_driver or plugged_in or self_check" > gpurun_out/r2_unvalidated.log 2>&1
+HNH_UNVALIDATED=1 timeout 900 python -m pytest tests -q -rfE -m gpu -k "als_cg_matches or null_and_empty or rectangular or dispatch_table or host_operands or hostpipe or gat or device_ or file_driver or plugged_in or self_check or harness" > gpurun_out/r2_unvalidated.log 2>&1
 echo "rc=$?" >> gpurun_out/r2_unvalidated.log; tail -n 40 gpurun_out/r2_unvalidated.log
 timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r2_pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/r2_pytest_gpu.log; tail -n 3 gpurun_out/r2_pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench_plain.json 2> gpurun_out/r2_bench_plain.err; tail -c 600 gpurun_out/r2_bench_plain.json

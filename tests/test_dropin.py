@@ -16,8 +16,9 @@ def test_reference_driver_compiles_unchanged():
     from distributed_sddmm_b200 import build
     exe = build.build_reference_driver()
     assert exe and os.path.exists(exe)
-    # bench_file.cpp, bench_heatmap.cpp, scratch.cpp
-    for other in ("bench_file_reference_main", "bench_heatmap_reference_main", "scratch_reference_main"):
+    # bench_file.cpp, bench_heatmap.cpp, scratch.cpp; bench_erdos_renyi.cpp + the reference's own benchmark_dist.cpp
+    for other in ("bench_file_reference_main", "bench_heatmap_reference_main", "scratch_reference_main",
+                  "bench_er_reference_harness"):
         assert os.path.exists(os.path.join(PKG, other)), other
     import torch
     if not torch.cuda.is_available():
@@ -103,3 +104,23 @@ def test_reference_self_check_program_runs_on_gpu(tmp_path):
             "SpMMA": float(((S @ X) ** 2).sum()), "SpMMB": float(((S.T @ X) ** 2).sum())}
     for k, v in want.items():
         assert abs(got[k] - v) <= 1e-5 * v, (k, got[k], v)  # the program prints 6 significant digits
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+def test_reference_benchmark_harness_runs_on_gpu(tmp_path):
+    """bench_erdos_renyi.cpp AND the reference's own benchmark_dist.cpp (benchmark_algorithm: algorithm selection,
+    benchmark inputs, five-trial loop, FLOP model, JSON record), both compiled unchanged, on this library's classes.
+    (`MPI_Barrier` of the compat layer drains the GPU streams, so the harness' wall clock covers the device work.)"""
+    path = os.path.join(PKG, "bench_er_reference_harness")
+    if not os.path.exists(path):
+        pytest.skip("bench_er_reference_harness not built")
+    out = tmp_path / "records.json"
+    p = subprocess.run([path, "12", "8", "15d", "32", "1", str(out)], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    records = json.loads("[" + out.read_text().strip().rstrip(",") + "]")
+    assert [r["alg_name"] for r in records] == ["15d_fusion1", "15d_fusion2"]
+    for r in records:
+        assert r["fused"] is True and r["num_trials"] == 5 and r["overall_throughput"] > 0 and r["elapsed"] > 0
+        assert r["alg_info"]["m"] == 4096 and r["alg_info"]["r"] == 32 and r["alg_info"]["p"] == 1
+        assert set(r["perf_stats"]) >= {"Computation Time"}
