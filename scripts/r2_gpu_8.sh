@@ -5,6 +5,7 @@ mkdir -p gpurun_out
 PORT=29517
 T() { PORT=$((PORT + 1)); timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $PORT "$@"; }
 timeout 900 python -m pytest tests/test_multirank_gpu.py -x -q -m gpu -k "all_operations" > gpurun_out/r2_pytest_mr8.log 2>&1; echo "rc=$?" >> gpurun_out/r2_pytest_mr8.log; tail -n 3 gpurun_out/r2_pytest_mr8.log
+HNH_UNVALIDATED=1 timeout 600 python -m pytest tests/test_dropin.py -q -rfE -m gpu -k "multi_process" > gpurun_out/r2_pytest_cpp_mp.log 2>&1; tail -n 5 gpurun_out/r2_pytest_cpp_mp.log
 for pieces in 1 2 4; do
   HNH_RING_PIECES=$pieces ALGS=15d_fusion2,15d_fusion1 CS=1 T scripts/scale_sweep.py > gpurun_out/r2_sweep8_pieces$pieces.log 2>&1
   grep '^{' gpurun_out/r2_sweep8_pieces$pieces.log | cut -c1-400

@@ -124,3 +124,29 @@ def test_reference_benchmark_harness_runs_on_gpu(tmp_path):
         assert r["fused"] is True and r["num_trials"] == 5 and r["overall_throughput"] > 0 and r["elapsed"] > 0
         assert r["alg_info"]["m"] == 4096 and r["alg_info"]["r"] == 32 and r["alg_info"]["p"] == 1
         assert set(r["perf_stats"]) >= {"Computation Time"}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
+@pytest.mark.parametrize("exe", ["bench_er_reference_main", "bench_er_reference_harness"])
+def test_cpp_driver_multi_process_nccl(exe, tmp_path):
+    """The reference's driver as `mpirun -n 2` would start it: two processes, one GPU each, the world built from the
+    torchrun-style environment and the NCCL id exchanged through HNH_NCCL_ID_FILE (hnh_world_init_from_env)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL does not put two ranks on one device)")
+    path = os.path.join(PKG, exe)
+    if not os.path.exists(path):
+        pytest.skip(f"{exe} not built")
+    out = tmp_path / "records.json"
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", HNH_NCCL_ID_FILE=str(tmp_path / "nccl.id"))
+        procs.append(subprocess.Popen([path, "12", "8", "15d", "32", "1", str(out)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    logs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(l[-1500:] for l in logs)
+    records = json.loads("[" + out.read_text().strip().rstrip(",") + "]")  # rank 0 writes
+    assert [r["alg_name"] for r in records] == ["15d_fusion1", "15d_fusion2"]
+    for r in records:
+        assert r["alg_info"]["p"] == 2 and r["num_trials"] == 5 and r["overall_throughput"] > 0
