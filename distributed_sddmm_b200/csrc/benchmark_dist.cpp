@@ -1,6 +1,9 @@
 // benchmark_dist.cpp -- benchmark_algorithm for the B200-native library (see the header).
 #include "hnh/benchmark_dist.hpp"
 
+#include <cstring>
+#include <ctime>
+
 #include <unistd.h>
 
 #include <cstdlib>
@@ -130,23 +133,54 @@ void hnh_world_init_from_env() {
     }
     const char *path = getenv("HNH_NCCL_ID_FILE");
     if (!path) throw hnh::Error(HNH_E_COMM, "WORLD_SIZE > 1 needs HNH_NCCL_ID_FILE (shared path for the NCCL unique id)");
+    // The file must belong to THIS launch: a leftover from an earlier run (or from a crash before the clean-up
+    // below) would hand the readers a dead id and ncclCommInitRank would hang.  Three guards: (1) the record
+    // carries a launch nonce (HNH_LAUNCH_ID, else TORCHELASTIC_RUN_ID, else MASTER_ADDR:MASTER_PORT) that the
+    // readers verify; (2) rank 0 unlinks the path before writing and again once every rank has joined the
+    // communicator; (3) with no nonce in the environment, a record written more than two minutes before the
+    // reader started is rejected as stale.
+    struct Record {
+        char magic[8];
+        char nonce[120];
+        int64_t written_at;
+        char id[HNHD_NCCL_ID_BYTES];
+    } rec;
+    string nonce;
+    if (const char *e = getenv("HNH_LAUNCH_ID")) nonce = e;
+    else if (const char *e2 = getenv("TORCHELASTIC_RUN_ID")) nonce = e2;
+    else if (getenv("MASTER_PORT")) nonce = string(getenv("MASTER_ADDR") ? getenv("MASTER_ADDR") : "") + ":" + getenv("MASTER_PORT");
+    if (nonce.size() >= sizeof rec.nonce) nonce.resize(sizeof rec.nonce - 1);
+    const int64_t started = (int64_t)time(nullptr);
     char id[HNHD_NCCL_ID_BYTES];
     if (rank == 0) {
+        unlink(path);
         hnh::Comm::nccl_unique_id(id);
-        string tmp = string(path) + ".tmp";
+        std::memset(&rec, 0, sizeof rec);
+        std::memcpy(rec.magic, "HNHNCCL1", 8);
+        std::memcpy(rec.nonce, nonce.c_str(), nonce.size());
+        rec.written_at = (int64_t)time(nullptr);
+        std::memcpy(rec.id, id, sizeof id);
+        string tmp = string(path) + ".tmp." + std::to_string((long long)getpid());
         std::ofstream f(tmp, std::ios::binary);
-        f.write(id, sizeof id);
+        f.write((const char *)&rec, sizeof rec);
         f.close();
-        rename(tmp.c_str(), path);
+        if (!f || rename(tmp.c_str(), path) != 0) throw hnh::Error(HNH_E_COMM, string("cannot write the NCCL id file ") + path);
     } else {
         for (int tries = 0;; tries++) {
             std::ifstream f(path, std::ios::binary);
-            if (f && f.read(id, sizeof id)) break;
-            if (tries > 6000) throw hnh::Error(HNH_E_COMM, "timed out waiting for the NCCL unique id file");
+            if (f && f.read((char *)&rec, sizeof rec) && std::memcmp(rec.magic, "HNHNCCL1", 8) == 0) {
+                rec.nonce[sizeof rec.nonce - 1] = 0;
+                const bool mine = nonce.empty() ? rec.written_at >= started - 120 : nonce == rec.nonce;
+                if (mine) break;  // otherwise: a stale record, rank 0 will replace it
+            }
+            if (tries > 6000) throw hnh::Error(HNH_E_COMM, "timed out waiting for this launch's NCCL unique id file");
             usleep(10000);
         }
+        std::memcpy(id, rec.id, sizeof id);
     }
     hnh::Comm::init_nccl(rank, size, id);
+    hnh::Comm::world()->barrier();  // every rank has read the record
+    if (rank == 0) unlink(path);
 }
 
 void hnh_world_finalize() {

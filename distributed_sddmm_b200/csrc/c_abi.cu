@@ -352,9 +352,16 @@ int hnh_spmm_f64(const int64_t *rowStart, const int64_t *col_idx, const double *
                  void *stream) {
     int v = validate_common(rowStart, col_idx, values, rows, nnz, r, "hnh_spmm_f64");
     if (v < 0) return v;
-    if (v == 1) return HNH_OK;
-    if (!X || !Y) return set_error(HNH_E_INVALID, "hnh_spmm_f64: null dense operand");
     cudaStream_t st = (cudaStream_t)stream;
+    if (v == 1) {
+        // BETA0 == "zero the output first": an empty block still has to leave Y = 0
+        if ((flags & HNH_FLAG_BETA0) && rows > 0) {
+            if (!Y) return set_error(HNH_E_INVALID, "hnh_spmm_f64: null dense operand");
+            return check_cuda(cudaMemsetAsync(Y, 0, sizeof(double) * (size_t)rows * r, st), "cudaMemsetAsync");
+        }
+        return HNH_OK;
+    }
+    if (!X || !Y) return set_error(HNH_E_INVALID, "hnh_spmm_f64: null dense operand");
     int rc = HNH_OK;
     bool beta0 = (flags & HNH_FLAG_BETA0) != 0;
     const bool a16 = aligned(X, 16) && aligned(Y, 16);
@@ -396,9 +403,16 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
                   void *stream) {
     int v = validate_common(rowStart, col_idx, values, rows, nnz, r, "hnh_fused_f64");
     if (v < 0) return v;
-    if (v == 1) return HNH_OK;
-    if (!X || !Y || !Out) return set_error(HNH_E_INVALID, "hnh_fused_f64: null dense operand");
     cudaStream_t st = (cudaStream_t)stream;
+    if (v == 1) {
+        // BETA0_OUT == "zero Out first": an empty block still has to leave Out = 0 (also in place, Out == X)
+        if ((flags & (HNH_FLAG_BETA0 | HNH_FLAG_BETA0_OUT)) && rows > 0) {
+            if (!Out) return set_error(HNH_E_INVALID, "hnh_fused_f64: null dense operand");
+            return check_cuda(cudaMemsetAsync(Out, 0, sizeof(double) * (size_t)rows * r, st), "cudaMemsetAsync");
+        }
+        return HNH_OK;
+    }
+    if (!X || !Y || !Out) return set_error(HNH_E_INVALID, "hnh_fused_f64: null dense operand");
     int rc = HNH_OK;
     const bool bv = (flags & (HNH_FLAG_BETA0 | HNH_FLAG_BETA0_VALUES)) != 0;
     const bool bo = (flags & (HNH_FLAG_BETA0 | HNH_FLAG_BETA0_OUT)) != 0;
@@ -531,10 +545,23 @@ int hnh_axpby_f64(double *dst, double alpha, const double *x, double beta, const
 
 int hnh_squared_norm_f64(double *out, const double *x, int64_t n, void *stream) {
     if (!out) return set_error(HNH_E_INVALID, "hnh_squared_norm_f64: null pointer");
-    int rc = check_cuda(cudaMemsetAsync(out, 0, sizeof(double), (cudaStream_t)stream), "cudaMemsetAsync");
+    if (n < 0) return set_error(HNH_E_INVALID, "hnh_squared_norm_f64: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return check_cuda(cudaMemsetAsync(out, 0, sizeof(double), st), "cudaMemsetAsync");
+    if (!x) return set_error(HNH_E_INVALID, "hnh_squared_norm_f64: null pointer");
+    int grid;
+    int rc = grid_for(squared_norm_partial_kernel, kBlock, kBlock * 4, n, &grid);
     if (rc) return rc;
-    if (n > 0 && !x) return set_error(HNH_E_INVALID, "hnh_squared_norm_f64: null pointer");
-    HNH_ELEMENTWISE_LAUNCH(squared_norm_kernel, n, out, x, n);
+    // per-call scratch, stream-ordered: concurrent calls on different streams never share partials
+    double *partial = nullptr;
+    rc = check_cuda(cudaMallocAsync((void **)&partial, sizeof(double) * (size_t)grid, st), "cudaMallocAsync");
+    if (rc) return rc;
+    squared_norm_partial_kernel<<<grid, kBlock, 0, st>>>(partial, x, n);
+    sum_partials_kernel<<<1, kBlock, 0, st>>>(out, partial, grid);
+    count_launch(2);
+    rc = check_cuda(cudaGetLastError(), "squared_norm launch");
+    cudaError_t e = cudaFreeAsync(partial, st);
+    return rc ? rc : check_cuda(e, "cudaFreeAsync");
 }
 
 // ---- host-buffer block API --------------------------------------------------------------------

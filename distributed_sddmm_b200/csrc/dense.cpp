@@ -141,6 +141,16 @@ void DenseMatrix::resize(int64_t rows, int64_t cols) {
     rows_ = rows;
     cols_ = cols;
 }
+void DenseMatrix::take(DenseMatrix &o) {
+    if (buf_.owns() && o.buf_.owns()) {
+        swap(o);
+        return;
+    }
+    require(o.size() == size(), "take: shape mismatch on a non-owning view");
+    if (size())
+        hnh::cuda_check(cudaMemcpyAsync(data(), o.data(), sizeof(double) * (size_t)size(), cudaMemcpyDeviceToDevice, cs()),
+                        "DenseMatrix::take");
+}
 void DenseMatrix::setConstant(double v) { abi_check(hnh_fill_f64(data(), size(), v, cs()), "fill"); }
 void DenseMatrix::setRandom(uint64_t seed) { abi_check(hnh_random_uniform_f64(data(), size(), seed, cs()), "random"); }
 DenseMatrix &DenseMatrix::operator*=(double s) {

@@ -1028,7 +1028,10 @@ __global__ void axpby_kernel(double *dst, double alpha, const double *x, double 
         dst[i] = alpha * x[i] + (y ? beta * y[i] : 0.0);
 }
 
-__global__ void squared_norm_kernel(double *out, const double *__restrict__ x, int64_t n) {
+// Deterministic two-pass sum of squares (fingerprints and residuals must be bit-stable run to run): pass 1 leaves
+// one partial per CTA (fixed grid-stride assignment, fixed shuffle tree), pass 2 -- one CTA -- adds the partials
+// in a fixed order.  No atomics.
+__global__ void squared_norm_partial_kernel(double *__restrict__ partial, const double *__restrict__ x, int64_t n) {
     __shared__ double warp_sums[8];
     double acc = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -1040,7 +1043,21 @@ __global__ void squared_norm_kernel(double *out, const double *__restrict__ x, i
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_sums[w];
-        atomicAdd(out, t);
+        partial[blockIdx.x] = t;
+    }
+}
+
+__global__ void sum_partials_kernel(double *__restrict__ out, const double *__restrict__ partial, int n) {
+    __shared__ double warp_sums[8];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+    acc = group_allreduce<32>(acc, 0xffffffffu);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += warp_sums[w];
+        *out = t;
     }
 }
 

@@ -66,8 +66,24 @@ bool PeerRing::all_shifts() {
 PeerRing::PeerRing(std::shared_ptr<Comm> ring, size_t slot_bytes) : ring_(std::move(ring)), bytes_(slot_bytes) {
     if (ring_->size() < 2) throw Error(HNH_E_INVALID, "PeerRing needs at least two ranks");
     // plain cudaMalloc: IPC handles need whole allocations that are never recycled for something else
-    for (int k = 0; k < 2; k++) cuda_check(cudaMalloc(&slot_[k], bytes_ ? bytes_ : 256), "cudaMalloc(ring slot)");
     owns_slots_ = true;
+    bool ok = true;
+    for (int k = 0; k < 2 && ok; k++)
+        if (cudaMalloc(&slot_[k], bytes_ ? bytes_ : 256) != cudaSuccess) {
+            cudaGetLastError();
+            slot_[k] = nullptr;
+            ok = false;
+        }
+    {  // collective: a rank that is out of memory must not leave the others waiting in connect()
+        int mine = ok ? 1 : 0;
+        std::vector<int> all((size_t)ring_->size());
+        ring_->host_allgather(&mine, all.data(), sizeof(int));
+        for (int v : all)
+            if (!v) {
+                release_all();
+                throw Error(HNH_E_ALLOC, "PeerRing: a rank could not allocate its ring slots");
+            }
+    }
     connect({{slot_[0], slot_[1]}}, -1);
 }
 
@@ -78,49 +94,103 @@ PeerRing::PeerRing(std::shared_ptr<Comm> ring, const std::vector<std::array<void
     connect(external, resident_slot);
 }
 
+// Construction is COLLECTIVE and so is its failure: every step that can fail on one rank only (allocation, IPC
+// export, IPC import -- e.g. a topology without uniform peer access) is followed by an exchange of ok-flags over
+// the ring, and either every rank goes on or every rank releases what it has acquired and throws.  A rank never
+// waits in the final barrier for a neighbour that has already fallen back to NCCL send/recv.
 void PeerRing::connect(const std::vector<std::array<void *, 2>> &local, int resident_slot) {
-    load_driver();
-    int dev = 0;
-    cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
-    cuda_check(cudaMalloc((void **)&flags_, 256), "cudaMalloc(ring flags)");
-    Flags init;
-    std::memset(&init, 0, sizeof init);
-    if (resident_slot == 0 || resident_slot == 1) {
-        init.arrived[resident_slot] = 1;
-        pushed_[resident_slot] = expected_[resident_slot] = 1;
-    }
-    cuda_check(cudaMemset(flags_, 0, 256), "cudaMemset");
-    cuda_check(cudaMemcpy(flags_, &init, sizeof init, cudaMemcpyHostToDevice), "cudaMemcpy(flags)");
-    cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    const int n = ring_->size(), me = ring_->rank();
+    const int dst = (me + 1) % n, src = (me + n - 1) % n;
+    std::string why;
+    auto agree = [&](bool ok_here, const char *stage) {
+        int mine = ok_here ? 1 : 0;
+        std::vector<int> all((size_t)n);
+        ring_->host_allgather(&mine, all.data(), sizeof(int));
+        for (int r = 0; r < n; r++)
+            if (!all[(size_t)r]) {
+                release_all();
+                throw Error(HNH_E_COMM, std::string("PeerRing: ") + stage + " failed on ring rank " + std::to_string(r) +
+                                            (r == me && !why.empty() ? " (" + why + ")" : std::string()));
+            }
+    };
 
     Handles mine;
     std::memset(&mine, 0, sizeof mine);
-    mine.nbuf = (int)local.size();
-    mine.device = dev;
-    for (size_t i = 0; i < local.size(); i++)
-        for (int k = 0; k < 2; k++) cuda_check(cudaIpcGetMemHandle(&mine.buf[i][k], local[i][(size_t)k]), "cudaIpcGetMemHandle");
-    cuda_check(cudaIpcGetMemHandle(&mine.flags, flags_), "cudaIpcGetMemHandle");
-    const int n = ring_->size(), me = ring_->rank();
+    bool ok = true;
+    try {
+        load_driver();
+        int dev = 0;
+        cuda_check(cudaGetDevice(&dev), "cudaGetDevice");
+        cuda_check(cudaMalloc((void **)&flags_, 256), "cudaMalloc(ring flags)");
+        Flags init;
+        std::memset(&init, 0, sizeof init);
+        if (resident_slot == 0 || resident_slot == 1) {
+            init.arrived[resident_slot] = 1;
+            pushed_[resident_slot] = expected_[resident_slot] = 1;
+        }
+        cuda_check(cudaMemset(flags_, 0, 256), "cudaMemset");
+        cuda_check(cudaMemcpy(flags_, &init, sizeof init, cudaMemcpyHostToDevice), "cudaMemcpy(flags)");
+        cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+        mine.nbuf = (int)local.size();
+        mine.device = dev;
+        for (size_t i = 0; i < local.size(); i++)
+            for (int k = 0; k < 2; k++) cuda_check(cudaIpcGetMemHandle(&mine.buf[i][k], local[i][(size_t)k]), "cudaIpcGetMemHandle");
+        cuda_check(cudaIpcGetMemHandle(&mine.flags, flags_), "cudaIpcGetMemHandle");
+    } catch (const Error &e) {
+        ok = false;
+        why = e.what();
+        cudaGetLastError();
+    }
+    agree(ok, "exporting the ring buffers");
+
     std::vector<Handles> all((size_t)n);
     ring_->host_allgather(&mine, all.data(), sizeof(Handles));
-    const int dst = (me + 1) % n, src = (me + n - 1) % n;
-    if (all[(size_t)dst].nbuf != mine.nbuf) throw Error(HNH_E_COMM, "PeerRing: ranks registered different buffer counts");
-    auto open = [&](const cudaIpcMemHandle_t &h) {
-        void *p = nullptr;
-        cuda_check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
-        return p;
-    };
-    dst_.resize(local.size());
-    for (size_t i = 0; i < local.size(); i++)
-        for (int k = 0; k < 2; k++) dst_[i][(size_t)k] = open(all[(size_t)dst].buf[i][k]);
-    dst_flags_ = (Flags *)open(all[(size_t)dst].flags);
-    if (src == dst) {
-        src_flags_ = dst_flags_;
-    } else {
-        src_flags_ = (Flags *)open(all[(size_t)src].flags);
-        src_flags_opened_ = true;
+    try {
+        if (all[(size_t)dst].nbuf != mine.nbuf) throw Error(HNH_E_COMM, "ranks registered different buffer counts");
+        auto open = [&](const cudaIpcMemHandle_t &h) {
+            void *p = nullptr;
+            cuda_check(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+            return p;
+        };
+        dst_.assign(local.size(), std::array<void *, 2>{nullptr, nullptr});
+        for (size_t i = 0; i < local.size(); i++)
+            for (int k = 0; k < 2; k++) dst_[i][(size_t)k] = open(all[(size_t)dst].buf[i][k]);
+        dst_flags_ = (Flags *)open(all[(size_t)dst].flags);
+        if (src == dst) {
+            src_flags_ = dst_flags_;
+        } else {
+            src_flags_ = (Flags *)open(all[(size_t)src].flags);
+            src_flags_opened_ = true;
+        }
+    } catch (const Error &e) {
+        ok = false;
+        why = e.what();
+        cudaGetLastError();
     }
+    agree(ok, "mapping the neighbours' ring buffers");
     ring_->barrier();
+}
+
+// Everything connect() / the constructors acquired (also on the failure path: the constructor throws, so the
+// destructor does not run).
+void PeerRing::release_all() {
+    for (auto &b : dst_)
+        for (int k = 0; k < 2; k++)
+            if (b[(size_t)k]) cudaIpcCloseMemHandle(b[(size_t)k]);
+    dst_.clear();
+    if (dst_flags_) cudaIpcCloseMemHandle(dst_flags_);
+    if (src_flags_opened_ && src_flags_) cudaIpcCloseMemHandle(src_flags_);
+    dst_flags_ = src_flags_ = nullptr;
+    src_flags_opened_ = false;
+    if (owns_slots_) {
+        cudaFree(slot_[0]);
+        cudaFree(slot_[1]);
+        slot_[0] = slot_[1] = nullptr;
+        owns_slots_ = false;
+    }
+    if (flags_) cudaFree(flags_);
+    flags_ = nullptr;
+    cudaGetLastError();
 }
 
 PeerRing::~PeerRing() {
@@ -130,16 +200,7 @@ PeerRing::~PeerRing() {
         ring_->barrier();
     } catch (...) {
     }
-    for (auto &b : dst_)
-        for (int k = 0; k < 2; k++)
-            if (b[(size_t)k]) cudaIpcCloseMemHandle(b[(size_t)k]);
-    if (dst_flags_) cudaIpcCloseMemHandle(dst_flags_);
-    if (src_flags_opened_ && src_flags_) cudaIpcCloseMemHandle(src_flags_);
-    if (owns_slots_) {
-        cudaFree(slot_[0]);
-        cudaFree(slot_[1]);
-    }
-    cudaFree(flags_);
+    release_all();
 }
 
 void PeerRing::begin_push(int k, cudaStream_t s) {

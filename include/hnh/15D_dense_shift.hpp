@@ -184,7 +184,7 @@ public:
         if (c > 1) {
             reduce_to(*stationary, accumulation_buffer);
         } else if (!in_place) {
-            stationary->swap(accumulation_buffer);  // instead of `*Arole = accumulation_buffer`
+            stationary->take(accumulation_buffer);  // instead of `*Arole = accumulation_buffer` (no copy unless a view)
         }
     }
 
@@ -286,7 +286,7 @@ private:
         }
         rt.chain(out, compute());
         hnh::cuda_check(cudaStreamSynchronize(out), "fusedSpMM_host");
-        stationary.swap(accumulation_buffer);  // the staging matrix holds the result, as after fusedSpMM
+        stationary.take(accumulation_buffer);  // the staging matrix holds the result, as after fusedSpMM
     }
     DenseMatrix gathered_riding;  // all p shards of the riding operand (fusedSpMM_host, p > 1)
 

@@ -154,7 +154,19 @@ public:
     vector<double> to_host() const;
     void copy_from_host(const double *h);
     void copy_to_host(double *h) const;  // synchronises
-    void swap(DenseMatrix &o) { buf_.swap(o.buf_); std::swap(rows_, o.rows_); std::swap(cols_, o.cols_); }
+    bool owns_storage() const { return buf_.owns(); }
+    // *this = o without reallocating when `o` can give its storage away (both own theirs and have one shape):
+    // a swap; otherwise (a view on either side) a device-to-device copy, like the reference's `*Arole = buffer`.
+    void take(DenseMatrix &o);
+    // Exchange storage with `o`.  The algorithm classes use this to hand a result back without a copy, so data()
+    // pointers (and view() / rowsView() windows) taken before an operation are invalid after it.  A non-owning
+    // view cannot take part: it would end up owning, or freeing, memory that belongs to somebody else.
+    void swap(DenseMatrix &o) {
+        if (!buf_.owns() || !o.buf_.owns()) throw hnh::Error(-1, "DenseMatrix::swap: non-owning view");
+        buf_.swap(o.buf_);
+        std::swap(rows_, o.rows_);
+        std::swap(cols_, o.cols_);
+    }
 
 private:
     hnh::DeviceBuffer<double> buf_;
@@ -184,7 +196,7 @@ public:
     void swapActive() { switchVal = 1 - switchVal; }
     void sync_active() {
         if (switchVal == 1) {
-            original->swap(*extra);
+            original->take(*extra);  // swap, or a copy when the caller's matrix is a non-owning view
             switchVal = 0;
         }
     }

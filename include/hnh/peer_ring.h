@@ -82,6 +82,7 @@ private:
     Flags *src_flags_ = nullptr;        // upstream's, IPC-mapped
     bool src_flags_opened_ = false;
     void connect(const std::vector<std::array<void *, 2>> &local, int resident_slot);
+    void release_all();  // idempotent; also the failure path of the (collective) constructors
     uint32_t pushed_[2] = {0, 0};    // shards I pushed into downstream slot k
     uint32_t expected_[2] = {0, 0};  // arrivals into my slot k that have been claimed
     uint32_t consumed_[2] = {0, 0};  // shards of my slot k that I have released

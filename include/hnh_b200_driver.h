@@ -114,7 +114,10 @@ int hnhd_dense_dummy_initialize(hnhd_alg_t *alg, hnhd_dense_t *m, int which); /*
 int hnhd_dense_from_host(hnhd_dense_t *m, const double *host); /* rows*cols doubles */
 int hnhd_dense_to_host(const hnhd_dense_t *m, double *host);
 int hnhd_dense_shape(const hnhd_dense_t *m, int64_t *rows, int64_t *cols);
-void *hnhd_dense_data(hnhd_dense_t *m); /* device pointer */
+/* Device pointer of the matrix storage.  NOT stable across operations: spmm / fusedSpMM / ring shifts may return
+ * their result by swapping the matrix's storage with an internal buffer (instead of the reference's copy-back,
+ * common.h:88-92), after which an earlier pointer refers to recycled memory.  Re-query after every operation. */
+void *hnhd_dense_data(hnhd_dense_t *m);
 void hnhd_dense_destroy(hnhd_dense_t *m);
 int hnhd_vec_create(int64_t n, double value, hnhd_vec_t **out);
 int hnhd_vec_like(hnhd_alg_t *alg, int which /*0=S,1=ST*/, double value, hnhd_vec_t **out);

@@ -85,6 +85,10 @@ def _bind(L):
     L.ref_time_fused.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
                                  C.c_int, P]
     L.ref_time_fused.restype = C.c_int64
+    if hasattr(L, "ref_time_fused_check"):
+        L.ref_time_fused_check.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int,
+                                           C.c_int, P, P]
+        L.ref_time_fused_check.restype = C.c_int64
     return L
 
 
@@ -185,6 +189,25 @@ def time_fused(alg, p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per
     nnz = lib().ref_time_fused(alg.encode(), p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per_rank,
                                secs.ctypes.data)
     return int(nnz), secs
+
+
+def pattern(rows, cols, salt, row0=0, col0=0):
+    """The position-dependent test operand of the parity legs (ref_driver.cpp::pattern_value): global rows
+    [row0, row0 + rows) x columns [col0, col0 + cols).  Exactly representable in fp64."""
+    i = np.arange(row0, row0 + rows, dtype=np.uint64)[:, None]
+    k = np.arange(col0, col0 + cols, dtype=np.uint64)[None, :]
+    h = (i * np.uint64(2654435761) + k * np.uint64(40503) + np.uint64(salt * 97)) & np.uint64(0xFFFFFFFF)
+    return h.astype(np.float64) / 4294967296.0 - 0.5
+
+
+def time_fused_check(alg, c, R, logM, nnz_per_row, seed, warmup, steps, threads):
+    """time_fused on ONE thread-rank plus the parity leg: one more fusedSpMM of the reference on A = pattern(1),
+    B = pattern(2).  Returns (dist_nnz, seconds[], result N x R)."""
+    secs = np.zeros(warmup + steps)
+    out = np.empty(((1 << logM), R))
+    nnz = lib().ref_time_fused_check(alg.encode(), c, R, logM, nnz_per_row, seed, warmup, steps, threads,
+                                     secs.ctypes.data, out.ctypes.data)
+    return int(nnz), secs, out
 
 
 def gat(alg, p, c, N, rows, cols, vals, layers, weights, alpha, X0, threads_per_rank: int = 1):

@@ -287,7 +287,14 @@ void ref_benchmark(const char *alg, int p, int c, int R, int logM, int nnz_per_r
 // Times (warmup + steps) calls of the reference's fusedSpMM(A, B, S, result, Amat) on its own
 // generator path with the benchmark's inputs (A = B = 0.001, S = 1: benchmark_dist.cpp:102-106).
 // seconds_out[warmup + steps]: wall seconds of every call (max over ranks).  Returns dist_nnz.
-struct TimeArgs { int logM, nnz_per_row, R, c, calls; const char *alg; double *secs; int64_t nnz; std::mutex mu; };
+struct TimeArgs { int logM, nnz_per_row, R, c, calls; const char *alg; double *secs; int64_t nnz; std::mutex mu;
+                  double *pattern_out = nullptr; };
+// Position-dependent test operand shared with bench.py's parity leg: exactly representable, so the CPU and the GPU
+// side start from bit-identical inputs.  salt 1 = A, salt 2 = B.
+static inline double pattern_value(uint64_t row, uint64_t col, uint64_t salt) {
+    const uint64_t h = (row * 2654435761ull + col * 40503ull + salt * 97ull) & 0xffffffffull;
+    return (double)h / 4294967296.0 - 0.5;
+}
 static void time_main(int rank, void *arg) {
     TimeArgs &a = *(TimeArgs *)arg;
     initialize_mpi_datatypes();
@@ -307,7 +314,27 @@ static void time_main(int rank, void *arg) {
         a.secs[t] = std::max(a.secs[t], dt);
     }
     if (rank == 0) a.nnz = (int64_t)S.dist_nnz;
+    if (a.pattern_out) {  // parity leg (one rank only): one more call on position-dependent operands, result exported
+        for (long i = 0; i < A.rows(); i++)
+            for (long k = 0; k < A.cols(); k++) A(i, k) = pattern_value((uint64_t)i, (uint64_t)k, 1);
+        for (long i = 0; i < B.rows(); i++)
+            for (long k = 0; k < B.cols(); k++) B(i, k) = pattern_value((uint64_t)i, (uint64_t)k, 2);
+        d->fusedSpMM(A, B, Sv, res, Amat);
+        std::memcpy(a.pattern_out, A.data(), sizeof(double) * (size_t)(A.rows() * A.cols()));
+    }
     delete d;
+}
+// ref_time_fused + the parity leg: p must be 1; pattern_out receives the N x R result of fusedSpMM(A, B, S, result,
+// Amat) of the REFERENCE on A = pattern(1), B = pattern(2) (see pattern_value).
+int64_t ref_time_fused_check(const char *alg, int c, int R, int logM, int nnz_per_row, uint64_t seed, int warmup, int steps,
+                             int threads_per_rank, double *seconds_out, double *pattern_out) {
+    hnh_shim_er_seed = seed;
+    TimeArgs a;
+    a.logM = logM; a.nnz_per_row = nnz_per_row; a.R = R; a.c = c; a.calls = warmup + steps; a.alg = alg; a.secs = seconds_out; a.nnz = 0;
+    a.pattern_out = pattern_out;
+    for (int t = 0; t < a.calls; t++) seconds_out[t] = 0.0;
+    hmpi_run(1, threads_per_rank, time_main, &a);
+    return a.nnz;
 }
 int64_t ref_time_fused(const char *alg, int p, int c, int R, int logM, int nnz_per_row, uint64_t seed, int warmup, int steps,
                        int threads_per_rank, double *seconds_out) {

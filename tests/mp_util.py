@@ -137,7 +137,19 @@ def compare_layout(got, want, alg):
                     assert len(g[f"{key}_b{b}_col_idx"]) == 0 and not np.any(g[f"{key}_b{b}_rowStart"]), (r, key, b, "empty block")
                     continue
                 for f in ("rowStart", "col_idx", "row_idx", "values"):
-                    assert np.array_equal(g[f"{key}_b{b}_{f}"], blk[f]), (r, key, b, f)
+                    have, ref_ = np.asarray(g[f"{key}_b{b}_{f}"]), np.asarray(blk[f])
+                    if f == "row_idx" and alg == "25d_dense_replicate" and not np.array_equal(have, ref_):
+                        # The reference's setup skew ships the block in `both` mode and never waits for the row_idx
+                        # receive (`else if`, SpmatLocal.hpp:248-255): whether its row_idx has
+                        # landed when the block is dumped is a race in the reference itself (seen on a 128-core box).
+                        # rowStart and col_idx (waited for, compared above) define the block; the delivered row_idx is
+                        # their expansion, which is what this library must hold.
+                        ref_ = np.repeat(np.arange(int(blk["rows"])), np.diff(np.asarray(blk["rowStart"])))
+                    if not np.array_equal(have, ref_):
+                        where = np.flatnonzero(have != ref_)[:6] if have.shape == ref_.shape else []
+                        raise AssertionError((r, key, b, f, f"shapes {have.shape} {ref_.shape}", f"first diffs at {list(where)}",
+                                              f"have {have[where].tolist() if len(where) else ''}",
+                                              f"want {ref_[where].tolist() if len(where) else ''}"))
 
 
 def compare_ops(got, want, script, rtol=1e-11):

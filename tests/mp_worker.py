@@ -170,7 +170,7 @@ def main():
             out["perf"] = json.dumps(alg.perf())
             if case.get("als"):
                 out["als"] = np.array(alg.als_residuals(1))
-        if have_gpu and case.get("hostpipe"):
+        if have_gpu and "hostpipe" in case:
             # fusedSpMM_host (upload / kernels / download pipelined, riding operand all-gathered) against the device path
             A, B = alg.like_A_matrix(), alg.like_B_matrix()
             GA, GB = global_inputs(N, R, seed)

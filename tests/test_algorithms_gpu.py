@@ -143,13 +143,7 @@ def test_als_cg_reduces_residual(world):
         assert np.isfinite([before, after]).all() and after < before, (name, before, after)
 
 
-# Paths written after this round's GPU budget was spent: compiled, never run on a device.  They are not on any
-# default code path; the first GPU session of the next round runs them with HNH_UNVALIDATED=1.
-unvalidated = pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1",
-                                 reason="not yet run on a GPU: set HNH_UNVALIDATED=1 (DESIGN.md section 7)")
-
-
-@unvalidated
+# (written at the end of round 1 without GPU time; first run green on a B200 in round 2, gates removed)
 @pytest.mark.parametrize("name,chunk", [("15d_fusion2", 77), ("15d_fusion2", 256), ("15d_fusion2", 4096),
                                         ("15d_fusion2", -1), ("15d_fusion1", 0), ("15d_sparse", 0)])
 def test_p1_fused_host_operands_match_device_path(world, problem, name, chunk):
@@ -177,7 +171,6 @@ def test_p1_fused_host_operands_match_device_path(world, problem, name, chunk):
         assert np.array_equal((A if mode == "A" else B).to_host(), want)
 
 
-@unvalidated
 def test_gat_device_helpers(world):
     """hnh_leaky_relu_f64 / hnh_relu_cols_f64 / hnh_dgemm_f64 against numpy."""
     import torch
@@ -206,7 +199,6 @@ def test_gat_device_helpers(world):
     assert rel_err(dC.cpu().numpy(), A @ B) < 1e-13
 
 
-@unvalidated
 @pytest.mark.parametrize("name", ALGS)
 def test_p1_gat_forward_matches_global_model(world, name):
     """GAT forward pass on one rank (every algorithm has full-width operands there) against the numpy model
@@ -232,7 +224,6 @@ def test_p1_gat_forward_matches_global_model(world, name):
     assert rel_err(net.buffer(1), orc.gat_forward_global(rows, cols, N, layers[:1], weights[:1], 0.2, X0)) < RTOL
 
 
-@unvalidated
 @pytest.mark.parametrize("name", ALGS)
 def test_p1_als_cg_matches_reference_als(world, name):
     """One alternating round of batched CG on given inputs against the reference's own Distributed_ALS (oracle/_ref)."""
@@ -253,7 +244,6 @@ def test_p1_als_cg_matches_reference_als(world, name):
     assert rel_err(A, want["A"]) < 1e-7 and rel_err(B, want["B"]) < 1e-7
 
 
-@unvalidated
 @pytest.mark.parametrize("R", [12, 192])
 def test_p1_fusion2_fused_widths_outside_the_dispatch_table(world, R):
     """fusedSpMM of the local-kernel-fusion algorithm on one rank at a width without an in-place kernel (the

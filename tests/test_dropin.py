@@ -45,7 +45,6 @@ def test_cpp_drivers_run_on_gpu(exe, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 def test_reference_file_driver_runs_on_gpu(tmp_path):
     """The reference's bench_file.cpp (MatrixMarket input, unfused SDDMM + SpMM on the 1.5D sparse-shift algorithm),
     compiled unchanged."""
@@ -69,7 +68,6 @@ def test_reference_file_driver_runs_on_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 def test_reference_self_check_program_runs_on_gpu(tmp_path):
     """The reference's scratch.cpp -- its only self-check: squared-norm fingerprints of sddmmA / spmmA / spmmB on
     dummyInitialize inputs with the 1.5D sparse-shift algorithm, then a GAT forward pass -- compiled unchanged.
@@ -107,7 +105,6 @@ def test_reference_self_check_program_runs_on_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 def test_reference_benchmark_harness_runs_on_gpu(tmp_path):
     """bench_erdos_renyi.cpp AND the reference's own benchmark_dist.cpp (benchmark_algorithm: algorithm selection,
     benchmark inputs, five-trial loop, FLOP model, JSON record), both compiled unchanged, on this library's classes.
@@ -127,7 +124,6 @@ def test_reference_benchmark_harness_runs_on_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("exe", ["bench_er_reference_main", "bench_er_reference_harness"])
 def test_cpp_driver_multi_process_nccl(exe, tmp_path):
     """The reference's driver as `mpirun -n 2` would start it: two processes, one GPU each, the world built from the

@@ -139,6 +139,17 @@ def test_empty_block_is_noop(hnh):
     assert gu.run_sddmm(csr, Y0, Y0).shape == (0,)
 
 
+def test_empty_block_with_overwrite_flags_zeroes_the_output(hnh):
+    """BETA0 == 'zero the output first' (hnh_b200.h): an empty block must leave Y / Out = 0, not stale."""
+    csr = orc.coo_to_csr(8, 8, np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0))
+    ones = np.ones((8, 16))
+    assert np.array_equal(gu.run_spmm(csr, np.zeros(0), ones, ones.copy(), flags=4), np.zeros((8, 16)))
+    _, out = gu.run_fused(csr, np.zeros(0), ones, ones, ones.copy(), flags=32)  # BETA0_OUT
+    assert np.array_equal(out, np.zeros((8, 16)))
+    _, out = gu.run_fused(csr, np.zeros(0), ones, ones, ones.copy(), flags=16)  # BETA0_VALUES only: Out kept
+    assert np.array_equal(out, ones)
+
+
 def test_unaligned_operands_fall_back_to_scalar_kernel(hnh):
     """Row pointers that are only 8-byte aligned (odd element offset) must still be correct."""
     R = 32
@@ -308,7 +319,6 @@ def test_tma_per_warp_variant_matches_direct(hnh, R):
         assert np.array_equal(v, vd) and np.array_equal(o, od)
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("logM,npr,lo,hi", [(10, 8, 0, 1024), (12, 32, 100, 3000), (6, 64, 0, 64), (14, 1, 5, 6)])
 def test_device_er_generator_is_bit_identical_with_host(logM, npr, lo, hi):
     """hnh_er_generate_device against hnh_er_generate_host (rows, columns, values, count); npr = 64 on 64 columns
@@ -332,7 +342,6 @@ def test_device_er_generator_is_bit_identical_with_host(logM, npr, lo, hi):
     assert L.hnh_er_generate_device(logM, npr, 1, lo, hi, dr.data_ptr(), dc.data_ptr(), dv.data_ptr(), 1, st) == -1 or n <= 1
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("transpose", [0, 1])
 @pytest.mark.parametrize("rows,cols,logM,npr", [(1024, 1024, 10, 8), (300, 4096, 12, 16), (1, 64, 6, 64), (512, 512, 9, 1)])
 def test_device_coo_to_csr_is_bit_identical_with_host(rows, cols, logM, npr, transpose):

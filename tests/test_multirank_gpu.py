@@ -76,7 +76,6 @@ GAT_CASES = {
 }
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_gat_forward_matches_reference(nproc):
     """GAT forward pass (include/hnh/gat.hpp) rank by rank against the reference's gat.hpp run by oracle/_ref --
@@ -111,7 +110,6 @@ HOSTPIPE_CASES = {
 }
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_fused_host_operands_multirank(nproc):
     """Distributed_Sparse::fusedSpMM_host on several ranks: bit-identical with upload + fusedSpMM + download (the blocks
@@ -137,7 +135,6 @@ ALS_CASES = {
 }
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_als_cg_matches_reference_als(nproc):
     """BASELINE.json config 5's caller: one alternating round of batched CG (10 iterations per side) on given ground
@@ -175,7 +172,6 @@ RECT_CASES = {
 }
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_rectangular_matrices_match_reference(nproc):
     """M != N (more columns than rows and the reverse, sizes that do not divide evenly): every public operation of
@@ -201,7 +197,6 @@ TINY_CASES = [U.case("15d_fusion1", 1, 4, 4, 1, name="nogolden_tiny_fusion1"), U
               U.case("25d_sparse_replicate", 1, 4, 4, 1, name="nogolden_tiny_25d_sparse")]
 
 
-@pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1")
 def test_null_and_empty_blocks_match_reference():
     """A 16 x 16 matrix with one nonzero per row on 4 ranks: most blocks are null or empty (the reference skips them,
     sparse_kernels.cpp:25-27,71-73,85-87); every operation must still agree with it."""

@@ -12,7 +12,6 @@ from oracle import hnh_oracle as orc
 from oracle import ref
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HNH_UNVALIDATED") != "1", reason="not yet run on a GPU: set HNH_UNVALIDATED=1"),
               pytest.mark.skipif(not (ref.available() and os.path.exists(ref.SO_CUDA)), reason="oracle/_ref builds are absent")]
 
 OPS = ["sddmmA", "spmmA", "spmmB", "fusedA", "sddmmB", "fusedB"]
