@@ -148,15 +148,15 @@ class ClockSampler:
                 "samples": len(self.samples), "reasons": sorted(self.reasons)}
 
 
-def workload_config(args, where, **extra):
-    cfg = {"workload": f"Erdos-Renyi N=2^{args.logM} nnz/row={args.nnz_per_row} r={args.R} FusedMM "
-                       f"(Sparse15D_Dense_Shift::fusedSpMM, {args.alg})",
-           "logM": args.logM, "nnz_per_row": args.nnz_per_row, "R": args.R, "algorithm": args.alg, "c": args.c,
-           "seed": SEED, "index_type": "int64", "where": where,
-           "l2": "per-GPU working set (dense shards + CSR) exceeds the 126 MB L2 and every step gathers "
-                 "from a different block; no explicit flush between steps"}
-    cfg.update(extra)
-    return cfg
+def workload_config(args):
+    """What is computed -- identical in the native and the reference arm (the driver compares the two dicts).
+    Everything that describes HOW a particular arm ran it (ranks, replication factor, transport, ...) is in `run`."""
+    return {"workload": f"Erdos-Renyi N=2^{args.logM} nnz/row={args.nnz_per_row} r={args.R} FusedMM "
+                        f"(Sparse15D_Dense_Shift::fusedSpMM, {args.alg}; A=B=0.001, S=1 as in benchmark_dist.cpp:102-106)",
+            "logM": args.logM, "nnz_per_row": args.nnz_per_row, "R": args.R, "algorithm": args.alg,
+            "seed": SEED, "index_type": "int64",
+            "l2": "working set (dense factors + CSR, > 1 GiB per GPU) exceeds the 126 MB L2 and every step gathers "
+                  "from a different block; no explicit flush between steps"}
 
 
 # ------------------------------------------------------------------ CPU arm ---------------
@@ -175,11 +175,12 @@ class _quiet_stdout:
         os.close(self.saved)
 
 
-def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
-    """GFLOP/s of the reference's fusedSpMM on the host cores (rank 0 only).  Uses oracle/_ref
-    (the reference's own code) when built, else the C port of its kernels.  The sample is the
-    whole configured matrix when that fits the time budget, otherwise the same configuration at
-    a smaller logM (same nnz/row and r: identical per-nonzero work)."""
+def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0, want_pattern=False):
+    """GFLOP/s of the reference's fusedSpMM on the host cores (rank 0 only).  Uses oracle/_ref (the reference's
+    own code) when built, else the C port of its kernels.  The sample is the whole configured matrix; `steps` is
+    reduced (never below 1) to keep warm-up + steps + set-up within `budget_s`, and only if even one step does not
+    fit is the same configuration run at a smaller logM (same nnz/row and r: identical per-nonzero work).
+    Returns (GFLOP/s, cores, kind, description, ms per step, steps timed, parity result or None)."""
     from oracle import ref
     cores = os.cpu_count() or 1
     try:
@@ -190,22 +191,29 @@ def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
         with _quiet_stdout():
             nnz0, s0 = ref.time_fused(args.alg, 1, 1, args.R, min(args.logM, 16), args.nnz_per_row, SEED, 1, 1, cores)
         gf0 = 4.0 * nnz0 * args.R / s0[-1] / 1e9
+        setup_calls = 6  # construction (redistribution, sorts, two COO->CSR) costs about six call-equivalents
         logM = args.logM
-        while logM > 16:
-            flop = 4.0 * (1 << logM) * args.nnz_per_row * args.R
-            # fusedSpMM calls + construction (redistribution, sorts, two COO->CSR), ~6 call-equivalents
-            if (warmup + steps + 6) * flop / (gf0 * 1e9) <= budget_s:
+        while True:
+            call_s = 4.0 * (1 << logM) * args.nnz_per_row * args.R / (gf0 * 1e9)
+            fit = int(budget_s / call_s) - setup_calls - warmup
+            if fit >= 1 or logM <= 16:
                 break
             logM -= 1
+        steps = max(1, min(steps, fit))
+        pattern_out = None
         with _quiet_stdout():
-            nnz, secs = ref.time_fused(args.alg, 1, 1, args.R, logM, args.nnz_per_row, SEED, warmup, steps, cores)
+            if want_pattern and logM == args.logM and hasattr(ref.lib(), "ref_time_fused_check"):
+                nnz, secs, pattern_out = ref.time_fused_check(args.alg, 1, args.R, logM, args.nnz_per_row, SEED, warmup,
+                                                              steps, cores)
+            else:
+                nnz, secs = ref.time_fused(args.alg, 1, 1, args.R, logM, args.nnz_per_row, SEED, warmup, steps, cores)
         per = secs[warmup:]
         gf = 4.0 * nnz * args.R / per / 1e9
         desc = (f"the reference's own code (oracle/_ref: reference sources compiled unmodified; MKL/MPI/Eigen/"
                 f"CombBLAS shimmed) {args.alg} p=1, {cores} OpenMP threads, Erdos-Renyi N=2^{logM} "
                 f"nnz/row={args.nnz_per_row} r={args.R} (nnz={nnz}), {len(per)} fusedSpMM calls after {warmup} warm-up, "
                 f"{np.mean(per)*1e3:.1f} ms each")
-        return float(np.mean(gf)), cores, "reference", desc, float(np.mean(per)) * 1e3
+        return float(np.mean(gf)), cores, "reference", desc, float(np.mean(per)) * 1e3, len(per), pattern_out
     # fall-back: C port of the two local kernels on a row sample
     from distributed_sddmm_b200 import lib
     from oracle import hnh_oracle as orc
@@ -228,25 +236,143 @@ def cpu_reference_fusedmm(args, warmup, steps, budget_s=45.0):
     gf = 4.0 * n * R / per / 1e9
     desc = (f"C port of the reference kernels (oracle/hnh_oracle.c; oracle/_ref not built), first {mrows} of {N} rows "
             f"against the full B, {orc.num_threads()} threads")
-    return float(np.mean(gf)), orc.num_threads(), "port", desc, float(np.mean(per)) * 1e3
+    return float(np.mean(gf)), orc.num_threads(), "port", desc, float(np.mean(per)) * 1e3, len(per), None
 
 
 def run_reference_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    steps, warmup = args.steps, min(args.warmup, 1)
-    # keep the whole run within a few minutes whatever K is: cap the number of timed calls
-    steps_run = min(steps, 5)
-    g, cores, kind, desc, ms = cpu_reference_fusedmm(args, warmup, steps_run, budget_s=90.0)
+    warmup = min(args.warmup, 1)
+    # every step is a full-size fusedSpMM of the reference (about 4 s on a 128-thread host): K of them when the run
+    # stays within a few minutes, fewer otherwise -- `steps` in the line is what was timed
+    g, cores, kind, desc, ms, steps_run, _ = cpu_reference_fusedmm(args, warmup, args.steps, budget_s=180.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": g, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": workload_config(args, "cpu", steps_timed=steps_run),
+        "impl": "reference", "metric": METRIC, "value": g, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": steps_run,
+        "steps_requested": args.steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "run": {"where": "cpu", "p": 1, "c": 1},
         "cpu_baseline": {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": g, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------ parity leg ------------
+PARITY_RTOL = 1e-5  # BASELINE.json north_star: fp64 values within 1e-5 relative
+
+
+def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
+    """One fusedSpMM on position-dependent operands (oracle/ref.py::pattern, exactly representable) at the FULL
+    benchmark size, on the data plane that was just timed (same algorithm object, same rings), checked two ways:
+      sample: `rows_per_rank` consecutive output rows of every rank against the C port of the reference kernels
+              (oracle/hnh_oracle.c, pinned bit-exact to the reference's loop) on the same tuples;
+      full  : every output row against one fusedSpMM of the reference's own code (oracle/_ref, p = 1) -- computed on
+              rank 0 and handed to the ranks over gloo.
+    Returns the `parity_check` object of the JSON line; never raises (a failure is reported, not hidden)."""
+    import torch
+    import torch.distributed as dist
+    from distributed_sddmm_b200 import lib
+    from oracle import hnh_oracle as orc
+    from oracle import ref
+    L = lib()
+    out = {"tolerance": PARITY_RTOL, "inputs": "A = pattern(1), B = pattern(2) (oracle/ref.py), S pattern all ones"}
+    try:
+        N, R = 1 << args.logM, args.R
+        (topA, leftA, nrA, ncA), (topB, leftB, nrB, ncB) = alg.submatrices("A")[0], alg.submatrices("B")[0]
+        hA = ref.pattern(nrA, ncA, 1, row0=topA, col0=leftA)
+        hB = ref.pattern(nrB, ncB, 2, row0=topB, col0=leftB)
+        hA[max(0, N - topA):] = 0.0  # padding rows beyond the matrix (none when p divides N)
+        hB[max(0, N - topB):] = 0.0
+        A.from_host(hA)
+        B.from_host(hB)
+        alg.fusedSpMM(A, B, Sv, res, "A")
+        got = A.to_host()
+        A.fill(0.001)
+        B.fill(0.001)
+        live = max(0, min(nrA, N - topA))
+
+        # ---- sample: the C port on this rank's rows [lo, hi) ----
+        n_s = min(live, 2048)
+        lo = topA + (live - n_s) // 3
+        cap = n_s * args.nnz_per_row
+        r_, c_, v_ = np.empty(cap, np.uint64), np.empty(cap, np.uint64), np.empty(cap, np.float64)
+        n = L.hnh_er_generate_host(args.logM, args.nnz_per_row, SEED, lo, lo + n_s, r_.ctypes.data, c_.ctypes.data,
+                                   v_.ctypes.data, cap)
+        r_, c_, v_ = r_[:n], c_[:n], v_[:n]
+        ucols, inv = np.unique(c_, return_inverse=True)
+        csr = orc.coo_to_csr(n_s, len(ucols), r_ - np.uint64(lo), inv.astype(np.uint64), v_)
+        Bs = ref.pattern_rows(ucols, R, 2)
+        As = ref.pattern(n_s, R, 1, row0=lo)
+        want = np.zeros((n_s, R))
+        orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), As, Bs, want)
+        have = got[lo - topA:lo - topA + n_s]
+        scale = max(float(np.abs(want).max()), 1e-300)
+        err_s = float(np.abs(have - want).max() / scale)
+        stats = torch.tensor([err_s, float(n_s), float(n)], dtype=torch.float64)
+        if world > 1:
+            worst = stats.clone()
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            tot = stats.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            err_s, rows_s, nnz_s = float(worst[0]), int(tot[1]), int(tot[2])
+        else:
+            rows_s, nnz_s = n_s, n
+        out["sample"] = {"checker": "oracle/hnh_oracle.c (C port of sparse_kernels.cpp:44-55 + CSR SpMM), same tuples",
+                         "rows": rows_s, "nnz": nnz_s, "max_rel_err": err_s}
+
+        # ---- full: the reference's own fusedSpMM ----
+        if want_full:
+            flag = torch.tensor([1 if (rank != 0 or pattern_ref is not None or
+                                       (ref.available() and hasattr(ref.lib(), "ref_time_fused_check"))) else 0])
+            if world > 1:
+                dist.broadcast(flag, src=0)
+            if int(flag[0]):
+                if rank == 0 and pattern_ref is None:
+                    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+                    with _quiet_stdout():
+                        _, _, pattern_ref = ref.time_fused_check(args.alg, 1, R, args.logM, args.nnz_per_row, SEED, 0, 0, cores)
+                if world > 1:  # hand every rank its rows (gloo send/recv, 64 MiB pieces)
+                    where = [None] * world
+                    dist.all_gather_object(where, (int(topA), int(live)))
+                    piece = max(1, (64 << 20) // (8 * R))
+                    if rank == 0:
+                        mine = pattern_ref[topA:topA + live]
+                        for dst_rank in range(1, world):
+                            top_r, live_r = where[dst_rank]
+                            for off in range(0, live_r, piece):
+                                m = min(piece, live_r - off)
+                                dist.send(torch.from_numpy(np.ascontiguousarray(pattern_ref[top_r + off:top_r + off + m])),
+                                          dst=dst_rank)
+                    else:
+                        mine = np.empty((live, R))
+                        for off in range(0, live, piece):
+                            m = min(piece, live - off)
+                            buf = torch.empty((m, R), dtype=torch.float64)
+                            dist.recv(buf, src=0)
+                            mine[off:off + m] = buf.numpy()
+                else:
+                    mine = pattern_ref[topA:topA + live]
+                loc = torch.tensor([float(np.abs(got[:live] - mine).max()), float(np.abs(mine).max())], dtype=torch.float64)
+                sq = torch.tensor([float(np.sum(got[:live] ** 2)), float(np.sum(mine ** 2))], dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(loc, op=dist.ReduceOp.MAX)
+                    dist.all_reduce(sq, op=dist.ReduceOp.SUM)
+                out["full"] = {"checker": "oracle/_ref (the reference's own sources, p = 1): one fusedSpMM on the same tuples "
+                                          "and operands", "rows": N, "max_rel_err": float(loc[0] / max(float(loc[1]), 1e-300)),
+                               "fingerprint_squared_norm": {"native": float(sq[0]), "reference": float(sq[1])}}
+            else:
+                out["full"] = None
+        errs = [out["sample"]["max_rel_err"]] + ([out["full"]["max_rel_err"]] if out.get("full") else [])
+        out["max_rel_err"] = max(errs)
+        out["n"] = (N if out.get("full") else rows_s)
+        out["pass"] = bool(np.isfinite(out["max_rel_err"]) and out["max_rel_err"] <= PARITY_RTOL)
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        out["error"] = f"{type(e).__name__}: {e}"
+        out["trace"] = traceback.format_exc()[-600:]
+        out["pass"] = False
+    return out
 
 
 # ------------------------------------------------------------------ GPU arm ---------------
@@ -353,7 +479,7 @@ def run_native(args):
     e2e_steps = max(2, min(args.steps, 5))
 
     def e2e_step():
-        if args.e2e_pipeline:
+        if not args.e2e_plain:
             alg.fusedSpMM_host(A, B, Sv, res, hA, hB, hO, "A")
             return
         D.check(L.hnhd_dense_from_host(A.h, hA.data_ptr()), "from_host")
@@ -372,15 +498,23 @@ def run_native(args):
     d2h = shapeA[0] * shapeA[1] * 8 * world
     e2e = {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "api": ("per rank: Distributed_Sparse::fusedSpMM_host (pinned host A, B in; result out)" if args.e2e_pipeline else
+           "api": ("per rank: Distributed_Sparse::fusedSpMM_host (pinned host A, B in; result out; uploads, kernels and "
+                   "download pipelined)" if not args.e2e_plain else
                    "per rank: DenseMatrix::copy_from_host(A), (B) from pinned memory; fusedSpMM; copy_to_host(A)")}
     del hA, hB, hO
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----
     cpu = None
+    pattern_ref = None
+    want_full = args.parity == "full"
     if world == 1 and not args.no_cpu_baseline:
-        g, cores, kind, desc, _ = cpu_reference_fusedmm(args, 1, 3)
+        g, cores, kind, desc, _, _, pattern_ref = cpu_reference_fusedmm(args, 1, 3, want_pattern=want_full)
         cpu = {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc}
+
+    # ---- parity leg (outside every timed region) ----
+    parity = None
+    if args.parity != "off":
+        parity = parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full)
 
     nvlink = None
     if world > 1:
@@ -396,12 +530,16 @@ def run_native(args):
             "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, "cuda", nnz=nnz, p=world, transport=("nccl" if world > 1 else "self"),
-                                      ring_steps=steps_ring, local_rows=alg.dims.localArows),
+            "config": workload_config(args),
+            "run": {"where": "cuda", "p": world, "c": c, "nnz": nnz, "ring_steps": steps_ring,
+                    "local_rows": alg.dims.localArows, "transport": info.get("transport"),
+                    "ring": alg.info().get("ring"),
+                    "collectives": ("NCCL all-gather / reduce-scatter over row_world" if c > 1 else "none")},
             "hbm_gbs_achieved_per_gpu": bytes_rank / (ms * 1e-3) / 1e9,
             "roofline": roofline,
             "phase_ms_per_step": {"computation": comp_ms, "cyclic_shift": shift_ms, "replication": repl_ms},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity_check": parity,
         }
         if other:
             line["other"] = other
@@ -426,9 +564,13 @@ def main():
     ap.add_argument("--alg", default="15d_fusion2", choices=["15d_fusion1", "15d_fusion2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other", action="store_true")
-    ap.add_argument("--e2e-pipeline", action="store_true",
-                    help="e2e leg through fusedSpMM_host (upload / kernel / download pipelined on one rank); "
-                         "off until the path has been validated on a GPU")
+    ap.add_argument("--e2e-plain", action="store_true",
+                    help="e2e leg as copy_from_host(A), (B); fusedSpMM; copy_to_host instead of the default "
+                         "Distributed_Sparse::fusedSpMM_host (upload / kernels / download pipelined)")
+    ap.add_argument("--parity", default="full", choices=["full", "sample", "off"],
+                    help="correctness leg after the timed loops (never timed): 'sample' = a row sample per rank against the "
+                         "C port of the reference kernels; 'full' = that plus every output row against one fusedSpMM of "
+                         "oracle/_ref (the reference's own code) on the same tuples and operands")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.c <= 0:

@@ -25,6 +25,7 @@ ABI = {
     "hnh_last_error_string": (C.c_char_p, []),
     "hnh_launch_count": (C.c_uint64, []),
     "hnh_sddmm_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, C.c_int, C.c_int, _P]),
+    "hnh_sddmm_scaled_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "hnh_sddmm_coo_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_spmm_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_fused_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
@@ -142,6 +143,7 @@ ABI.update({
     "hnhd_alg_destroy": (None, [_P]),
     "hnhd_alg_dims": (C.c_int, [_P, C.POINTER(AlgDims)]),
     "hnhd_alg_submatrices": (C.c_int, [_P, C.c_int, _P, C.c_int]),
+    "hnhd_setup_times_json": (C.c_int, [C.c_char_p, _SZ, C.c_int]),
     "hnhd_alg_info_json": (C.c_int, [_P, C.c_char_p, _SZ]),
     "hnhd_alg_perf_json": (C.c_int, [_P, C.c_char_p, _SZ]),
     "hnhd_alg_reset_timers": (C.c_int, [_P]),

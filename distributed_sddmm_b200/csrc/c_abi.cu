@@ -82,12 +82,13 @@ constexpr int kBlock = 256;
 // ---- templated launchers ------------------------------------------------------------------
 template <int R, int G, int VW, int UN>
 int launch_sddmm(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
-                 const double *X, const double *Y, bool beta0, cudaStream_t st) {
+                 const double *X, const double *Y, bool beta0, const double *scale, double *scaled_out, bool sv,
+                 cudaStream_t st) {
     int grid;
     auto k = beta0 ? sddmm_row_kernel<R, G, VW, UN, true> : sddmm_row_kernel<R, G, VW, UN, false>;
     int rc = grid_for(k, kBlock, kBlock / G, rows, &grid);
     if (rc) return rc;
-    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y);
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, scale, scaled_out, sv);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "sddmm_row_kernel launch");
 }
@@ -129,12 +130,13 @@ int launch_sddmm_coo(const int64_t *row_idx, const int64_t *col_idx, double *val
 // ---- small-r ("split") launchers: G = GK*GN lanes per row ----------------------------------
 template <int R, int GK, int GN, int VW, int UN>
 int launch_sddmm_split(const int64_t *rowStart, const int64_t *col_idx, double *values,
-                       int64_t rows, const double *X, const double *Y, bool beta0, cudaStream_t st) {
+                       int64_t rows, const double *X, const double *Y, bool beta0, const double *scale, double *scaled_out,
+                       bool sv, cudaStream_t st) {
     int grid;
     auto k = beta0 ? sddmm_split_kernel<R, GK, GN, VW, UN, true> : sddmm_split_kernel<R, GK, GN, VW, UN, false>;
     int rc = grid_for(k, kBlock, kBlock / (GK * GN), rows, &grid);
     if (rc) return rc;
-    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y);
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, scale, scaled_out, sv);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "sddmm_split_kernel launch");
 }
@@ -186,13 +188,14 @@ static int split_max_r() {
 // ---- TMA-staged launchers (HNH_FLAG_TMA_STAGE; r in {128, 256}, 16-byte aligned X) ------------
 template <int R, bool FUSED>
 int launch_tma(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows, const double *X,
-               const double *Y, double *Out, bool bv, bool bo, cudaStream_t st) {
+               const double *Y, double *Out, bool bv, bool bo, cudaStream_t st, const double *scale = nullptr,
+               double *scaled_out = nullptr, bool sv = false) {
     int grid;
     auto k = bv ? (bo ? tma_row_kernel<R, 4, FUSED, true, true> : tma_row_kernel<R, 4, FUSED, true, false>)
                 : (bo ? tma_row_kernel<R, 4, FUSED, false, true> : tma_row_kernel<R, 4, FUSED, false, false>);
     int rc = grid_for(k, kBlock, 8, rows, &grid);
     if (rc) return rc;
-    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out, scale, scaled_out, sv);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "tma_row_kernel launch");
 }
@@ -202,13 +205,14 @@ int launch_tma(const int64_t *rowStart, const int64_t *col_idx, double *values, 
 // of a CTA wait for the longest of their rows).  HNH_TMA=0 / 1 forces one or the other everywhere.
 template <int R, bool FUSED>
 int launch_tma_warp(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows, const double *X,
-                    const double *Y, double *Out, bool bv, bool bo, cudaStream_t st) {
+                    const double *Y, double *Out, bool bv, bool bo, cudaStream_t st, const double *scale = nullptr,
+                    double *scaled_out = nullptr, bool sv = false) {
     int grid;
     auto k = bv ? (bo ? tma_warp_kernel<R, 4, FUSED, true, true> : tma_warp_kernel<R, 4, FUSED, true, false>)
                 : (bo ? tma_warp_kernel<R, 4, FUSED, false, true> : tma_warp_kernel<R, 4, FUSED, false, false>);
     int rc = grid_for(k, kBlock, 8, rows, &grid);
     if (rc) return rc;
-    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out, scale, scaled_out, sv);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "tma_warp_kernel launch");
 }
@@ -262,9 +266,11 @@ const char *hnh_last_error_string(void) { return g_err; }
 
 uint64_t hnh_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
-                  int64_t nnz, const double *X, const double *Y, int r, int flags, void *stream) {
+int hnh_sddmm_scaled_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
+                         int64_t nnz, const double *X, const double *Y, int r, int flags, const double *scale,
+                         double *scaled_out, void *stream) {
     int v = validate_common(rowStart, col_idx, values, rows, nnz, r, "hnh_sddmm_f64");
+    if (scaled_out && !scale) return set_error(HNH_E_INVALID, "hnh_sddmm_scaled_f64: scaled_out without scale");
     if (v < 0) return v;
     if (v == 1) return HNH_OK;
     if (!X || !Y) return set_error(HNH_E_INVALID, "hnh_sddmm_f64: null dense operand");
@@ -273,7 +279,7 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
     bool beta0 = (flags & HNH_FLAG_BETA0) != 0;
     const bool a16 = aligned(X, 16) && aligned(Y, 16);
     const bool a32 = aligned(X, 32) && aligned(Y, 32);
-#define S4(R, G, VW, UN) rc = launch_sddmm<R, G, VW, UN>(rowStart, col_idx, values, rows, X, Y, beta0, st)
+#define S4(R, G, VW, UN) rc = launch_sddmm<R, G, VW, UN>(rowStart, col_idx, values, rows, X, Y, beta0, scale, scaled_out, sv, st)
 #define SGEN                                                                                 \
     {                                                                                        \
         int grid;                                                                            \
@@ -286,14 +292,26 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         }                                                                                    \
     }
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
+    // The epilogue form needs a table kernel and distinct arrays (scale is read through the read-only path); otherwise
+    // the product is one more elementwise pass after the plain SDDMM.
+    if (scale && ((flags & HNH_FLAG_FORCE_GENERIC) || !a16 || !table_r || (const double *)scaled_out == scale || values == scale)) {
+        rc = hnh_sddmm_scaled_f64(rowStart, col_idx, values, rows, nnz, X, Y, r, flags & ~HNH_FLAG_SCALE_VALUES, nullptr, nullptr, stream);
+        if (rc) return rc;
+        if (scaled_out) {
+            rc = hnh_hadamard_f64(scaled_out, scale, values, nnz, stream);
+            if (rc || !(flags & HNH_FLAG_SCALE_VALUES)) return rc;
+        }
+        return hnh_hadamard_f64(values, scale, values, nnz, stream);
+    }
+    const bool sv = (flags & HNH_FLAG_SCALE_VALUES) != 0;
     if ((flags & HNH_FLAG_TMA_WARP) && a32 && (r == 128 || r == 256) && !(flags & HNH_FLAG_FORCE_GENERIC)) {
-        return r == 128 ? launch_tma_warp<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st)
-                        : launch_tma_warp<256, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st);
+        return r == 128 ? launch_tma_warp<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st, scale, scaled_out, sv)
+                        : launch_tma_warp<256, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st, scale, scaled_out, sv);
     }
     if (((flags & HNH_FLAG_TMA_STAGE) || (tma_default(false, r, beta0) && !(flags & HNH_FLAG_FORCE_DIRECT))) && a32 &&
         (r == 128 || r == 256) && !(flags & HNH_FLAG_FORCE_GENERIC)) {
-        return r == 128 ? launch_tma<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st)
-                        : launch_tma<256, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st);
+        return r == 128 ? launch_tma<128, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st, scale, scaled_out, sv)
+                        : launch_tma<256, false>(rowStart, col_idx, values, rows, X, Y, nullptr, beta0, false, st, scale, scaled_out, sv);
     }
     if ((flags & HNH_FLAG_FORCE_GENERIC) || !a16 || !table_r) {
         if (beta0) {  // the any-r kernel accumulates: clear first
@@ -303,7 +321,7 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         SGEN
     } else if (r <= split_max_r() && r <= 32) {
 #define SP(R, GK, GN, VW, UN) \
-    rc = launch_sddmm_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, beta0, st)
+    rc = launch_sddmm_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, beta0, scale, scaled_out, sv, st)
         HNH_DISPATCH_SPLIT(r, a32, SP)
 #undef SP
     } else {
@@ -312,6 +330,11 @@ int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
 #undef S4
 #undef SGEN
     return rc;
+}
+
+int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
+                  int64_t nnz, const double *X, const double *Y, int r, int flags, void *stream) {
+    return hnh_sddmm_scaled_f64(rowStart, col_idx, values, rows, nnz, X, Y, r, flags, nullptr, nullptr, stream);
 }
 
 int hnh_sddmm_coo_f64(const int64_t *row_idx, const int64_t *col_idx, double *values,

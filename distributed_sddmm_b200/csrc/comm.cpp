@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "hnh/runtime.h"
 #include "hnh_b200.h"
@@ -21,6 +22,21 @@ public:
     virtual void allgather(int rank, int size, const void *send, void *recv, size_t bytes_each, cudaStream_t s) = 0;
     virtual void reduce_scatter(int rank, int size, const double *send, double *recv, size_t count_each, cudaStream_t s) = 0;
     virtual void allreduce(double *buf, size_t count, cudaStream_t s) = 0;
+    // default: through host memory with the transport's host all-to-all
+    virtual void alltoallv(int rank, int size, const void *send, const size_t *sb, const size_t *sd, void *recv, const size_t *rb,
+                           const size_t *rd, cudaStream_t s) {
+        size_t stot = 0, rtot = 0;
+        for (int i = 0; i < size; i++) {
+            stot = std::max(stot, sd[i] + sb[i]);
+            rtot = std::max(rtot, rd[i] + rb[i]);
+        }
+        std::vector<char> hs(std::max<size_t>(stot, 1)), hr(std::max<size_t>(rtot, 1));
+        if (stot) cuda_check(cudaMemcpyAsync(hs.data(), send, stot, cudaMemcpyDeviceToHost, s), "alltoallv d2h");
+        cuda_check(cudaStreamSynchronize(s), "alltoallv sync");
+        host_alltoallv(rank, size, hs.data(), sb, sd, hr.data(), rb, rd);
+        if (rtot) cuda_check(cudaMemcpyAsync(recv, hr.data(), rtot, cudaMemcpyHostToDevice, s), "alltoallv h2d");
+        cuda_check(cudaStreamSynchronize(s), "alltoallv sync");
+    }
     virtual void host_sendrecv(int rank, const void *send, size_t sb, int dst, void *recv, size_t rb, int src) = 0;
     virtual void host_allgather(int rank, int size, const void *send, void *recv, size_t bytes_each) = 0;
     virtual void host_alltoallv(int rank, int size, const void *send, const size_t *sb, const size_t *sd,
@@ -54,6 +70,11 @@ public:
         copy_d2d(recv, send, c * sizeof(double), s);
     }
     void allreduce(double *, size_t, cudaStream_t) override {}
+    void alltoallv(int, int, const void *send, const size_t *sb, const size_t *sd, void *recv, const size_t *rb, const size_t *rd,
+                   cudaStream_t s) override {
+        if (sb[0] != rb[0]) throw Error(HNH_E_COMM, "self alltoallv: size mismatch");
+        copy_d2d((char *)recv + rd[0], (const char *)send + sd[0], sb[0], s);
+    }
     void host_sendrecv(int, const void *send, size_t sb, int, void *recv, size_t rb, int) override {
         if (sb != rb) throw Error(HNH_E_COMM, "self sendrecv: size mismatch");
         if (recv != send) std::memcpy(recv, send, sb);
@@ -112,6 +133,17 @@ public:
         nccl_check(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, comm_, s), "ncclAllReduce");
     }
 
+    void alltoallv(int rank, int size, const void *send, const size_t *sb, const size_t *sd, void *recv, const size_t *rb,
+                   const size_t *rd, cudaStream_t s) override {
+        copy_d2d((char *)recv + rd[rank], (const char *)send + sd[rank], sb[rank], s);
+        nccl_check(ncclGroupStart(), "ncclGroupStart");
+        for (int i = 0; i < size; i++) {
+            if (i == rank) continue;
+            if (sb[i]) nccl_check(ncclSend((const char *)send + sd[i], sb[i], ncclChar, i, comm_, s), "ncclSend");
+            if (rb[i]) nccl_check(ncclRecv((char *)recv + rd[i], rb[i], ncclChar, i, comm_, s), "ncclRecv");
+        }
+        nccl_check(ncclGroupEnd(), "ncclGroupEnd");
+    }
     // host buffers are staged through device memory (setup path only)
     void host_sendrecv(int rank, const void *send, size_t sb, int dst, void *recv, size_t rb, int src) override {
         if (dst == rank && src == rank) {
@@ -303,6 +335,12 @@ void Comm::allgather(const void *send, void *recv, size_t b, cudaStream_t s) {
 void Comm::reduce_scatter_sum_f64(const double *send, double *recv, size_t c, cudaStream_t s) {
     bytes_sent_ += c * sizeof(double) * (size_ - 1);
     t_->reduce_scatter(rank_, size_, send, recv, c, s);
+}
+void Comm::alltoallv(const void *send, const size_t *sb, const size_t *sd, void *recv, const size_t *rb, const size_t *rd,
+                     cudaStream_t s) {
+    for (int i = 0; i < size_; i++)
+        if (i != rank_) bytes_sent_ += sb[i];
+    t_->alltoallv(rank_, size_, send, sb, sd, recv, rb, rd, s);
 }
 void Comm::allreduce_sum_f64(double *buf, size_t count, cudaStream_t s) {
     if (size_ > 1) bytes_sent_ += 2 * count * sizeof(double) * (size_ - 1) / size_;

@@ -103,6 +103,71 @@ __global__ void csr_row_start_kernel(const uint64_t *__restrict__ sorted_key, in
     }
 }
 
+// ---- device-resident tuple pipeline (SpmatLocal::redistribute_nonzeros and friends) -------------------------
+// owner of tuple i from a (row block, column block) table that the host filled by calling the distribution's
+// blockOwner() for every block pair (NonzeroDistribution::getOwner, reference SpmatLocal.hpp:45-52)
+__global__ void tuple_owner_kernel(const uint64_t *__restrict__ r, const uint64_t *__restrict__ c, int64_t n, int transpose,
+                                   uint64_t rows_in_block, uint64_t cols_in_block, const int *__restrict__ table,
+                                   int64_t table_rows, int64_t table_cols, unsigned *__restrict__ owner,
+                                   int64_t *__restrict__ idx, int *bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t rb = (transpose ? c[i] : r[i]) / rows_in_block, cb = (transpose ? r[i] : c[i]) / cols_in_block;
+        int o = 0;
+        if (rb >= (uint64_t)table_rows || cb >= (uint64_t)table_cols) *bad = 1;
+        else o = table[rb * (uint64_t)table_cols + cb];
+        if (o < 0) { *bad = 1; o = 0; }
+        owner[i] = (unsigned)o;
+        idx[i] = i;
+    }
+}
+
+__global__ void iota_kernel(int64_t *__restrict__ idx, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) idx[i] = i;
+}
+
+// out[p] = in[perm[p]] for the three tuple arrays; swap_rc exchanges the roles of r and c on the way
+__global__ void tuple_gather_kernel(const uint64_t *__restrict__ r, const uint64_t *__restrict__ c, const double *__restrict__ v,
+                                    const int64_t *__restrict__ perm, int64_t n, int swap_rc, uint64_t *__restrict__ r_out,
+                                    uint64_t *__restrict__ c_out, double *__restrict__ v_out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+        const int64_t i = perm[p];
+        r_out[p] = swap_rc ? c[i] : r[i];
+        c_out[p] = swap_rc ? r[i] : c[i];
+        v_out[p] = v[i];
+    }
+}
+
+__global__ void key_gather_kernel(const uint64_t *__restrict__ key, const int64_t *__restrict__ perm, int64_t n,
+                                  uint64_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) out[p] = key[perm[p]];
+}
+
+__global__ void tuple_mod_kernel(uint64_t *__restrict__ r, uint64_t *__restrict__ c, int64_t n, uint64_t mod_r, uint64_t mod_c) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (mod_r) r[i] %= mod_r;
+        if (mod_c) c[i] %= mod_c;
+    }
+}
+
+// starts[k] = first position with key[p] >= k * width (keys ascending), k = 0 .. divisions
+template <typename K>
+__global__ void lower_bounds_kernel(const K *__restrict__ key, int64_t n, uint64_t width, int divisions, int64_t *__restrict__ starts) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > divisions) return;
+    const uint64_t want = (uint64_t)k * width;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((uint64_t)key[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    starts[k] = lo;
+}
+
 int grid_for(int64_t n) {
     int sms = 148;
     hnh::device_sm_count(&sms);
@@ -111,7 +176,7 @@ int grid_for(int64_t n) {
 }
 
 struct Scratch {  // cudaMalloc'ed temporaries of one call, released on every exit path
-    void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *p[12] = {};
     int n = 0;
     cudaError_t get(void **out, size_t bytes) {
         cudaError_t e = cudaMalloc(out, std::max<size_t>(bytes, 256));
@@ -213,6 +278,131 @@ int hnh_coo_to_csr_device(int64_t rows, int64_t cols, int64_t nnz, const uint64_
     count_launch(2);
     rc = check_cuda(cudaGetLastError(), "csr kernels launch");
     if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");  // the scratch is freed on return
+    return rc;
+}
+
+// ---- device-resident tuple pipeline ------------------------------------------------------------------------------
+int hnh_tuples_bucket_by_owner_device(const uint64_t *r, const uint64_t *c, const double *v, int64_t n, int transpose,
+                                      int64_t rows_in_block, int64_t cols_in_block, const int *owner_table_host,
+                                      int64_t table_rows, int64_t table_cols, int nbuckets, uint64_t *r_out, uint64_t *c_out,
+                                      double *v_out, int64_t *starts_host, void *stream) {
+    if (n < 0 || nbuckets < 1 || rows_in_block < 1 || cols_in_block < 1 || table_rows < 1 || table_cols < 1 || !owner_table_host ||
+        !starts_host)
+        return set_error(HNH_E_INVALID, "hnh_tuples_bucket_by_owner_device: bad argument");
+    if (n > INT32_MAX) return set_error(HNH_E_INVALID, "hnh_tuples_bucket_by_owner_device: more than 2^31 - 1 tuples");
+    for (int b = 0; b <= nbuckets; b++) starts_host[b] = 0;
+    if (n == 0) return HNH_OK;
+    if (!r || !c || !v || !r_out || !c_out || !v_out) return set_error(HNH_E_INVALID, "hnh_tuples_bucket_by_owner_device: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch s;
+    int *table = nullptr, *bad = nullptr;
+    unsigned *owner = nullptr, *owner_sorted = nullptr;
+    int64_t *idx = nullptr, *idx_sorted = nullptr, *starts = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    const size_t tb = sizeof(int) * (size_t)(table_rows * table_cols);
+    int rc = check_cuda(s.get((void **)&table, tb), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&bad, sizeof(int)), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&owner, sizeof(unsigned) * (size_t)n), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&owner_sorted, sizeof(unsigned) * (size_t)n), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&idx, sizeof(int64_t) * (size_t)n), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&idx_sorted, sizeof(int64_t) * (size_t)n), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&starts, sizeof(int64_t) * (size_t)(nbuckets + 1)), "cudaMalloc");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(table, owner_table_host, tb, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaMemsetAsync(bad, 0, sizeof(int), st), "cudaMemsetAsync");
+    if (rc) return rc;
+    tuple_owner_kernel<<<grid_for(n), kThreads, 0, st>>>(r, c, n, transpose, (uint64_t)rows_in_block, (uint64_t)cols_in_block, table,
+                                                         table_rows, table_cols, owner, idx, bad);
+    count_launch(1);
+    const int end_bit = bits_for((uint64_t)std::max(nbuckets - 1, 1));
+    rc = check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, owner, owner_sorted, idx, idx_sorted, (int)n, 0, end_bit, st),
+                    "cub sort size");
+    if (!rc) rc = check_cuda(s.get(&tmp, tmp_bytes), "cudaMalloc");
+    if (!rc) rc = check_cuda(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, owner, owner_sorted, idx, idx_sorted, (int)n, 0, end_bit, st),
+                             "cub sort");
+    if (rc) return rc;
+    tuple_gather_kernel<<<grid_for(n), kThreads, 0, st>>>(r, c, v, idx_sorted, n, transpose, r_out, c_out, v_out);
+    lower_bounds_kernel<unsigned><<<(nbuckets + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(owner_sorted, n, 1, nbuckets, starts);
+    count_launch(2);
+    int host_bad = 0;
+    rc = check_cuda(cudaMemcpyAsync(&host_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(starts_host, starts, sizeof(int64_t) * (size_t)(nbuckets + 1), cudaMemcpyDeviceToHost, st),
+                             "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    if (rc) return rc;
+    if (host_bad) return set_error(HNH_E_INVALID, "hnh_tuples_bucket_by_owner_device: a coordinate has no owner (outside the block table)");
+    return HNH_OK;
+}
+
+int hnh_tuples_sort_colmajor_device(uint64_t *r, uint64_t *c, double *v, int64_t n, uint64_t max_r, uint64_t max_c, void *stream) {
+    if (n < 0) return set_error(HNH_E_INVALID, "hnh_tuples_sort_colmajor_device: bad argument");
+    if (n > INT32_MAX) return set_error(HNH_E_INVALID, "hnh_tuples_sort_colmajor_device: more than 2^31 - 1 tuples");
+    if (n <= 1) return HNH_OK;
+    if (!r || !c || !v) return set_error(HNH_E_INVALID, "hnh_tuples_sort_colmajor_device: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch s;
+    uint64_t *key_a = nullptr, *key_b = nullptr, *r2 = nullptr, *c2 = nullptr;
+    double *v2 = nullptr;
+    int64_t *idx_a = nullptr, *idx_b = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0, tb2 = 0;
+    const size_t b8 = sizeof(uint64_t) * (size_t)n;
+    int rc = check_cuda(s.get((void **)&key_a, b8), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&key_b, b8), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&idx_a, b8), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&idx_b, b8), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&r2, b8), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&c2, b8), "cudaMalloc");
+    if (!rc) rc = check_cuda(s.get((void **)&v2, b8), "cudaMalloc");
+    if (rc) return rc;
+    const int bits_r = bits_for(std::max<uint64_t>(max_r, 1)), bits_c = bits_for(std::max<uint64_t>(max_c, 1));
+    rc = check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, key_a, key_b, idx_a, idx_b, (int)n, 0, bits_r, st), "cub sort size");
+    if (!rc) rc = check_cuda(cub::DeviceRadixSort::SortPairs(nullptr, tb2, key_a, key_b, idx_a, idx_b, (int)n, 0, bits_c, st), "cub sort size");
+    tmp_bytes = std::max(tmp_bytes, tb2);
+    if (!rc) rc = check_cuda(s.get(&tmp, tmp_bytes), "cudaMalloc");
+    if (rc) return rc;
+    // LSD over the pair: stable by row first, then stable by column  =>  ordered by (column, row), ties in input order
+    iota_kernel<<<grid_for(n), kThreads, 0, st>>>(idx_a, n);
+    rc = check_cuda(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, r, key_b, idx_a, idx_b, (int)n, 0, bits_r, st), "cub sort (rows)");
+    if (rc) return rc;
+    key_gather_kernel<<<grid_for(n), kThreads, 0, st>>>(c, idx_b, n, key_a);
+    rc = check_cuda(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_a, key_b, idx_b, idx_a, (int)n, 0, bits_c, st), "cub sort (cols)");
+    if (rc) return rc;
+    tuple_gather_kernel<<<grid_for(n), kThreads, 0, st>>>(r, c, v, idx_a, n, 0, r2, c2, v2);
+    count_launch(3);
+    rc = check_cuda(cudaMemcpyAsync(r, r2, b8, cudaMemcpyDeviceToDevice, st), "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(c, c2, b8, cudaMemcpyDeviceToDevice, st), "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaMemcpyAsync(v, v2, b8, cudaMemcpyDeviceToDevice, st), "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+    return rc;
+}
+
+int hnh_tuples_mod_device(uint64_t *r, uint64_t *c, int64_t n, uint64_t mod_r, uint64_t mod_c, void *stream) {
+    if (n < 0) return set_error(HNH_E_INVALID, "hnh_tuples_mod_device: bad argument");
+    if (n == 0 || (mod_r == 0 && mod_c == 0)) return HNH_OK;
+    if (!r || !c) return set_error(HNH_E_INVALID, "hnh_tuples_mod_device: null pointer");
+    tuple_mod_kernel<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(r, c, n, mod_r, mod_c);
+    count_launch(1);
+    return check_cuda(cudaGetLastError(), "tuple_mod_kernel launch");
+}
+
+int hnh_tuples_block_starts_device(const uint64_t *c_sorted, int64_t n, uint64_t block_width, int divisions, int64_t *starts_host,
+                                   void *stream) {
+    if (n < 0 || divisions < 0 || block_width == 0 || !starts_host) return set_error(HNH_E_INVALID, "hnh_tuples_block_starts_device: bad argument");
+    if (n == 0) {
+        for (int k = 0; k <= divisions; k++) starts_host[k] = 0;
+        return HNH_OK;
+    }
+    if (!c_sorted) return set_error(HNH_E_INVALID, "hnh_tuples_block_starts_device: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    Scratch s;
+    int64_t *starts = nullptr;
+    int rc = check_cuda(s.get((void **)&starts, sizeof(int64_t) * (size_t)(divisions + 1)), "cudaMalloc");
+    if (rc) return rc;
+    lower_bounds_kernel<uint64_t><<<(divisions + 1 + kThreads - 1) / kThreads, kThreads, 0, st>>>(c_sorted, n, block_width, divisions, starts);
+    count_launch(1);
+    rc = check_cuda(cudaMemcpyAsync(starts_host, starts, sizeof(int64_t) * (size_t)(divisions + 1), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync");
+    if (!rc) rc = check_cuda(cudaStreamSynchronize(st), "cudaStreamSynchronize");
     return rc;
 }
 

@@ -70,6 +70,12 @@ json Distributed_Sparse::json_algorithm_info() {
     }
     j["nnz_procs"] = nnz;
     j["nnz_tpose_procs"] = nnz_t;
+    // not in the reference's record: what actually carries the ring shifts of this object
+    j["transport"] = hnh::Comm::world()->transport_name();
+    j["peer_rings"] = (int)(peer_rings_.size() + sparse_rings_.size());
+    j["ring"] = p == 1 ? "none" : (!peer_rings_.empty() || !sparse_rings_.empty())
+                                      ? "peer_ring (copy engines into CUDA-IPC mapped peer slots, stream memory-op flags)"
+                                      : "send/recv of the transport";
     return j;
 }
 

@@ -84,6 +84,17 @@ int hnhd_world_size(void) { return hnh::Comm::world_initialised() ? hnh::Comm::w
 int hnhd_barrier(void) { return guarded([] { hnh::Comm::world()->barrier(); }); }
 int hnhd_device_synchronize(void) { return guarded([] { hnh::Runtime::get().sync_all(); }); }
 
+int hnhd_setup_times_json(char *out, size_t capacity, int reset) {
+    int n = 0;
+    int rc = guarded([&] {
+        json j = json::object();
+        for (auto &kv : hnh::setup_times()) j[kv.first] = kv.second;
+        n = copy_json(j, out, capacity);
+        if (reset) hnh::setup_times_reset();
+    });
+    return rc ? rc : n;
+}
+
 // ---- SpmatLocal ---------------------------------------------------------------------------------
 int hnhd_spmat_load_er(int logM, int nnz_per_row, uint64_t seed, hnhd_spmat_t **out) {
     return guarded([&] {
@@ -116,11 +127,15 @@ int hnhd_spmat_info(const hnhd_spmat_t *S, uint64_t *M, uint64_t *N, uint64_t *d
     if (M) *M = S->m.M;
     if (N) *N = S->m.N;
     if (dist_nnz) *dist_nnz = S->m.dist_nnz;
-    if (local_tuples) *local_tuples = (int64_t)S->m.coords.size();
+    if (local_tuples) *local_tuples = S->m.local_tuple_count();
     return HNH_OK;
 }
 int hnhd_spmat_tuples(const hnhd_spmat_t *S, uint64_t *rows, uint64_t *cols, double *vals, int64_t capacity) {
-    if (!S || (int64_t)S->m.coords.size() > capacity) return hnh::set_error(HNH_E_INVALID, "bad argument / capacity");
+    if (!S || S->m.local_tuple_count() > capacity) return hnh::set_error(HNH_E_INVALID, "bad argument / capacity");
+    if (S->m.tuples_on_device()) {
+        int rc = guarded([&] { const_cast<hnhd_spmat_t *>(S)->m.tuples_to_host(); });
+        if (rc) return rc;
+    }
     for (size_t i = 0; i < S->m.coords.size(); i++) {
         rows[i] = S->m.coords[i].r;
         cols[i] = S->m.coords[i].c;

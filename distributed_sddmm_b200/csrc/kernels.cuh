@@ -109,13 +109,30 @@ __device__ __forceinline__ double group_allreduce(double d, unsigned mask) {
     return d;
 }
 
+// SDDMM epilogue.  Plain: values[j] = d.  With `scale` (the caller's S values, aligned with `values`) the Hadamard
+// product of the reference's `SValues.cwiseProduct(getCSRValues())` (15D_dense_shift.hpp:364-368) is applied at the
+// only moment the finished dot is in a register: scaled_out[j] = scale[j] * d (the user-visible SDDMM result); with
+// scale but no scaled_out (or with scale_values) the scaled value replaces d in `values` itself (what the fused SDDMM -> SpMM of the
+// replication-reuse strategy wants: the SpMM pass then reads the CSR values directly, no setCSRValues copy).
+__device__ __forceinline__ void sddmm_store(double *__restrict__ values, const double *__restrict__ scale,
+                                            double *__restrict__ scaled_out, bool scale_values, int64_t j, double d) {
+    if (scale != nullptr) {
+        const double sd = ld_stream_f64(scale + j) * d;
+        if (scaled_out != nullptr) scaled_out[j] = sd;
+        values[j] = (scale_values || scaled_out == nullptr) ? sd : d;
+    } else {
+        values[j] = d;
+    }
+}
+
 // ------------------------------------------------------------------ K1: SDDMM ------------
 // values[j] += X[row] . Y[col_idx[j]] for every nonzero j of every CSR row.
 template <int R, int G, int VW, int UN, bool BETA0>
 __global__ void __launch_bounds__(256)
 sddmm_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
                  double *__restrict__ values, int64_t rows, const double *__restrict__ X,
-                 const double *__restrict__ Y) {
+                 const double *__restrict__ Y, const double *__restrict__ scale, double *__restrict__ scaled_out,
+                 bool scale_values) {
     constexpr int NV = R / (G * VW);
     static_assert(NV * G * VW == R, "R must equal NV*G*VW");
     const int lane = threadIdx.x & 31;
@@ -163,8 +180,8 @@ sddmm_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
                 }
             }
             if (gl < cnt) {
-                if (BETA0) values[j + gl] = mine;
-                else values[j + gl] += mine;
+                if (!BETA0) mine += values[j + gl];
+                sddmm_store(values, scale, scaled_out, scale_values, j + gl, mine);
             }
         }
     }
@@ -366,7 +383,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 template <int R, int UN, bool FUSED, bool BV, bool BO>
 __global__ void __launch_bounds__(256)
 tma_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx, double *__restrict__ values,
-               int64_t rows, const double *X, const double *__restrict__ Y, double *Out) {
+               int64_t rows, const double *X, const double *__restrict__ Y, double *Out, const double *__restrict__ scale,
+               double *__restrict__ scaled_out, bool scale_values) {
     constexpr int G = 32, VW = 4, TR = 8;
     constexpr int NV = R / (G * VW);
     static_assert(NV * G * VW == R, "R must be a multiple of 128");
@@ -457,7 +475,10 @@ tma_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__
                     }
                 }
             }
-            if (lane < cnt) values[j + lane] = myval;
+            if (lane < cnt) {
+                if (FUSED) values[j + lane] = myval;
+                else sddmm_store(values, scale, scaled_out, scale_values, j + lane, myval);
+            }
         }
         if (FUSED) {
 #pragma unroll
@@ -474,7 +495,8 @@ tma_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__
 template <int R, int UN, bool FUSED, bool BV, bool BO>
 __global__ void __launch_bounds__(256)
 tma_warp_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx, double *__restrict__ values,
-                int64_t rows, const double *X, const double *__restrict__ Y, double *Out) {
+                int64_t rows, const double *X, const double *__restrict__ Y, double *Out, const double *__restrict__ scale,
+               double *__restrict__ scaled_out, bool scale_values) {
     constexpr int G = 32, VW = 4, NW = 8;
     constexpr int NV = R / (G * VW);
     static_assert(NV * G * VW == R, "R must be a multiple of 128");
@@ -565,7 +587,10 @@ tma_warp_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict_
                     }
                 }
             }
-            if (lane < cnt) values[j + lane] = myval;
+            if (lane < cnt) {
+                if (FUSED) values[j + lane] = myval;
+                else sddmm_store(values, scale, scaled_out, scale_values, j + lane, myval);
+            }
         }
         if (FUSED) {
 #pragma unroll
@@ -600,7 +625,8 @@ template <int R, int GK, int GN, int VW, int UN, bool BETA0>
 __global__ void __launch_bounds__(256)
 sddmm_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
                    double *__restrict__ values, int64_t rows, const double *__restrict__ X,
-                   const double *__restrict__ Y) {
+                   const double *__restrict__ Y, const double *__restrict__ scale, double *__restrict__ scaled_out,
+                 bool scale_values) {
     constexpr int G = GK * GN;
     constexpr int NV = R / (GK * VW);
     static_assert(NV * GK * VW == R && G <= 32, "bad split shape");
@@ -646,7 +672,7 @@ sddmm_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restri
 #pragma unroll
                     for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
                 d = reduce_over_k<G, GK>(d, gmask);
-                if (j < e && kp == 0) values[j] = vold[u] + d;
+                if (j < e && kp == 0) sddmm_store(values, scale, scaled_out, scale_values, j, vold[u] + d);
             }
         }
     }

@@ -1,6 +1,9 @@
 // runtime.cpp -- implementation of hnh::Runtime, EventTimers and the error helpers.
 #include "hnh/runtime.h"
 
+#include <chrono>
+#include <cstdlib>
+
 #include "hnh_b200.h"
 
 namespace hnh {
@@ -13,6 +16,26 @@ void cuda_check(cudaError_t e, const char *what) {
 
 void abi_check(int rc, const char *what) {
     if (rc != HNH_OK) throw Error(rc, std::string(what) + ": " + hnh_last_error_string());
+}
+
+namespace {
+std::map<std::string, double> g_setup_times;
+double wall_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+void setup_time_add(const std::string &phase, double seconds) { g_setup_times[phase] += seconds; }
+std::map<std::string, double> setup_times() { return g_setup_times; }
+void setup_times_reset() { g_setup_times.clear(); }
+SetupPhase::SetupPhase(std::string name) : phase(std::move(name)), t0(wall_now()) {}
+SetupPhase::~SetupPhase() { setup_time_add(phase, wall_now() - t0); }
+bool device_setup_enabled(int64_t items) {
+    static const int forced = [] {
+        const char *e = getenv("HNH_DEVICE_SETUP");
+        return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+    }();
+    if (forced == 0 || !Runtime::get().has_device()) return false;
+    return forced == 1 || items >= ((int64_t)1 << 18);
 }
 
 Runtime &Runtime::get() {

@@ -15,8 +15,18 @@ size_t StandardKernel::sddmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B
     const double *Y = blk->transpose ? A.data() : B.data();
     CSRHandle *h = blk->getActive();
     int f = flags | (values_are_zero ? HNH_FLAG_BETA0 : 0);
-    abi_check(hnh_sddmm_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords, X, Y,
-                            (int)A.cols(), f, Runtime::get().compute_stream()),
+    const double *scale = nullptr;
+    double *scaled_out = nullptr;
+    if (sddmm_scale != nullptr) {
+        const int64_t off = (int64_t)S.blockStarts[(size_t)block];
+        if (off + blk->num_coords > sddmm_scale->size() || (sddmm_scaled_out && off + blk->num_coords > sddmm_scaled_out->size()))
+            throw hnh::Error(HNH_E_INVALID, "sddmm_local: the S value vectors are shorter than the local sparse matrix");
+        scale = sddmm_scale->data() + off;
+        if (sddmm_scaled_out) scaled_out = sddmm_scaled_out->data() + off;
+        if (sddmm_scale_values) f |= HNH_FLAG_SCALE_VALUES;
+    }
+    abi_check(hnh_sddmm_scaled_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords, X, Y,
+                                   (int)A.cols(), f, scale, scaled_out, Runtime::get().compute_stream()),
               "hnh_sddmm_f64");
     return 0;
 }

@@ -308,6 +308,15 @@ class Algorithm:
             pass
 
 
+def setup_times(reset: bool = False) -> dict:
+    """Wall-clock seconds of this process' setup phases so far (hnh::SetupPhase)."""
+    buf = C.create_string_buffer(1 << 14)
+    n = lib().hnhd_setup_times_json(buf, len(buf), int(reset))
+    if n < 0:
+        check(n, "hnhd_setup_times_json")
+    return json.loads(buf.value.decode())
+
+
 def timer_start():
     check(lib().hnhd_timer_start(), "timer_start")
 

@@ -68,9 +68,9 @@ public:
         localise(*ST, localBrows * c, localArows);
         const bool local_tpose = fusionApproach == 1;
         S->initializeCSRBlocks(localArows * c, localBrows, -1, local_tpose);
-        vector<spcoord_t>().swap(S->coords);
+        S->release_tuples();
         ST->initializeCSRBlocks(localBrows * c, localArows, -1, local_tpose);
-        vector<spcoord_t>().swap(ST->coords);
+        ST->release_tuples();
         check_initialized();
     }
 
@@ -115,10 +115,14 @@ public:
         if (initial_replicate && c > 1) replicate(*stationary, accumulation_buffer);
         DenseMatrix &fixed = c > 1 ? accumulation_buffer : *stationary;
 
+        // StandardKernel: the SDDMM overwrites the block values (every block is met once per pass) and applies the
+        // Hadamard product with SValues in its epilogue (reference: a separate pass, :364-368)
+        const bool fold = sddmm && sk != nullptr;
         region_begin("Computation Time", compute());
         if (sddmm) {
-            if (!sk) choice->setValuesConstant(0.0);  // StandardKernel overwrites instead (every block is met once)
-        } else {
+            if (!sk) choice->setValuesConstant(0.0);
+            if (fold) prepare_sddmm_result(*sddmm_result_ptr, SValues, *choice);
+        } else if (!spmm_values_resident_) {
             choice->setCSRValues(SValues);
         }
         region_end("Computation Time", compute());
@@ -129,14 +133,29 @@ public:
         // the riding matrix is written only by the fusion-1 SpMM (it is the output there)
         const bool riding_is_input = sddmm || fusionApproach == 2;
 
+        if (fold) {
+            sk->sddmm_scale = &SValues;
+            sk->sddmm_scaled_out = sddmm_result_ptr;
+            sk->sddmm_scale_values = fused_pass_;  // the SpMM pass of a FusedMM reads S o dots from the CSR values
+        }
         ring_dense(*riding, grid->col_world, riding_is_input, "Cyclic Shift Time", "Computation Time",
                    [&](int step, DenseMatrix &shard) {
-                       if (sk) sk->values_are_zero = sddmm;
+                       if (sk) {
+                           sk->values_are_zero = sddmm;
+                           // fusion-1 SpMM: the riding shard is the output; at step 0 it is this rank's own, still
+                           // all zeros (the caller's setZero is skipped when the hint is on)
+                           sk->output_is_zero = !sddmm && riding_output_is_zero_ && step == 0;
+                       }
                        kernel->triple_function(local_mode, *choice, fixed, shard, block_at(step), 0);
-                       if (sk) sk->values_are_zero = false;
+                       if (sk) sk->values_are_zero = sk->output_is_zero = false;
                    });
+        if (fold) {
+            sk->sddmm_scale = nullptr;
+            sk->sddmm_scaled_out = nullptr;
+            sk->sddmm_scale_values = false;
+        }
 
-        if (sddmm) {
+        if (sddmm && !fold) {
             region_begin("Computation Time", compute());
             hadamard_values(*sddmm_result_ptr, SValues, *choice);
             region_end("Computation Time", compute());
@@ -151,7 +170,24 @@ public:
     void fusedSpMM(DenseMatrix &localA, DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer,
                    MatMode mode) override {
         if (fusionApproach == 1) {
-            Distributed_Sparse::fusedSpMM(localA, localB, Svalues, sddmm_buffer, mode);
+            // "replication reuse" (reference distributed_sparse.h:289-312): an SDDMM pass, then an SpMM pass that skips
+            // the replication.  With StandardKernel the value plumbing between the two is gone: the SDDMM epilogue
+            // leaves Svalues o dots both in sddmm_buffer and in the CSR values (no Hadamard pass, no setCSRValues
+            // copy), and the first kernel of the SpMM pass overwrites its output (no zero-fill pass, no read of zeros).
+            if (dynamic_cast<StandardKernel *>(kernel) == nullptr) {
+                Distributed_Sparse::fusedSpMM(localA, localB, Svalues, sddmm_buffer, mode);
+                return;
+            }
+            fused_pass_ = true;
+            try {
+                algorithm(localA, localB, Svalues, &sddmm_buffer, mode == Amat ? k_sddmmA : k_sddmmB, true);
+                spmm_values_resident_ = riding_output_is_zero_ = true;
+                algorithm(localA, localB, sddmm_buffer, nullptr, mode == Amat ? k_spmmA : k_spmmB, false);
+            } catch (...) {
+                fused_pass_ = spmm_values_resident_ = riding_output_is_zero_ = false;
+                throw;
+            }
+            fused_pass_ = spmm_values_resident_ = riding_output_is_zero_ = false;
             return;
         }
         DenseMatrix *stationary = mode == Amat ? &localA : &localB;
@@ -244,6 +280,16 @@ public:
 
 private:
     static bool in_place_width(int64_t r) { return r >= 4 && r <= 256 && (r & (r - 1)) == 0; }
+    // state of a fusion-1 FusedMM in flight (see fusedSpMM)
+    bool fused_pass_ = false, spmm_values_resident_ = false, riding_output_is_zero_ = false;
+
+    // the checks and sizing hadamard_values() does, for the epilogue form of the product
+    static void prepare_sddmm_result(VectorXd &result, VectorXd &SValues, SpmatLocal &m) {
+        const int64_t total = (int64_t)m.blockStarts.back();
+        if (SValues.size() != total)
+            throw hnh::Error(-1, "SValues has " + to_string(SValues.size()) + " entries, the local sparse matrix " + to_string(total));
+        if (result.size() != total) result.resize(total);
+    }
 
     // p > 1, c = 1: see fusedSpMM_host.  Block b of this rank's block row multiplies the shard owned by rank b of
     // the column communicator (block_at(step) with c = 1 is (rankInCol - step) mod p, the owner of the shard the
@@ -291,8 +337,7 @@ private:
     DenseMatrix gathered_riding;  // all p shards of the riding operand (fusedSpMM_host, p > 1)
 
     static void localise(SpmatLocal &m, int block_rows, int block_cols) {
-#pragma omp parallel for
-        for (int64_t i = 0; i < (int64_t)m.coords.size(); i++) m.coords[i].r %= (uint64_t)block_rows;
+        m.mod_coordinates((uint64_t)block_rows, 0);
         m.divideIntoBlockCols(block_cols, hnh::Comm::world()->size(), true);
         m.own_all_coordinates();
     }

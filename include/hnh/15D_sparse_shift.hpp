@@ -184,16 +184,15 @@ public:
 private:
     // localise rows, exchange per-rank nnz along the ring, build the single CSR block
     vector<int> make_monolith(SpmatLocal &m, int block_height, int ncols) {
-#pragma omp parallel for
-        for (int64_t i = 0; i < (int64_t)m.coords.size(); i++) m.coords[i].r %= (uint64_t)block_height;
+        m.mod_coordinates((uint64_t)block_height, 0);
         vector<int> nnz_in_axis((size_t)(p / c));
-        int mine = (int)m.coords.size();
+        int mine = (int)m.local_tuple_count();
         grid->col_world->host_allgather(&mine, nnz_in_axis.data(), sizeof(int));
         const int max_nnz = *std::max_element(nnz_in_axis.begin(), nnz_in_axis.end());
         m.own_all_coordinates();
         m.monolithBlockColumn();
         m.initializeCSRBlocks(block_height, ncols, max_nnz, false);
-        vector<spcoord_t>().swap(m.coords);
+        m.release_tuples();
         return nnz_in_axis;
     }
 };

@@ -247,18 +247,14 @@ public:
 private:
     vector<int> build_block(SpmatLocal &m, int block_rows, int block_cols) {
         vector<int> nnz_in_axis((size_t)sqrtpc);
-        int mine = (int)m.coords.size();
+        int mine = (int)m.local_tuple_count();
         grid->row_world->host_allgather(&mine, nnz_in_axis.data(), sizeof(int));
         const int max_nnz = *std::max_element(nnz_in_axis.begin(), nnz_in_axis.end());
-#pragma omp parallel for
-        for (int64_t i = 0; i < (int64_t)m.coords.size(); i++) {
-            m.coords[i].r %= (uint64_t)block_rows;
-            m.coords[i].c %= (uint64_t)block_cols;
-        }
+        m.mod_coordinates((uint64_t)block_rows, (uint64_t)block_cols);
         m.own_all_coordinates();
         m.monolithBlockColumn();
         m.initializeCSRBlocks(block_rows, block_cols, max_nnz, true);
-        vector<spcoord_t>().swap(m.coords);
+        m.release_tuples();
         return nnz_in_axis;
     }
 

@@ -194,6 +194,7 @@ private:
     // floor layer -> all layers of the fiber; each layer then owns one segment of the values
     int replicate_block(SpmatLocal &m, int block_rows, int block_cols) {
         hnh::Comm &fiber = *grid->fiber_world;
+        m.tuples_to_host();  // the fiber broadcast below works on the host tuples
         uint64_t n = m.coords.size();
         vector<uint64_t> counts((size_t)fiber.size());
         fiber.host_allgather(&n, counts.data(), sizeof(uint64_t));

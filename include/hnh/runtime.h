@@ -66,6 +66,22 @@ private:
     std::map<size_t, std::vector<void *>> cache_;
 };
 
+// Wall-clock phases of the (untimed) setup path -- tuple generation, redistribution (bucket, exchange, sort),
+// COO -> CSR -- accumulated per process; `where` says which side did the heavy lifting ("host" / "device").
+// Read through hnhd_setup_times_json(); reset with setup_times_reset().
+void setup_time_add(const std::string &phase, double seconds);
+std::map<std::string, double> setup_times();
+void setup_times_reset();
+struct SetupPhase {  // RAII: adds its lifetime to `phase`
+    std::string phase;
+    double t0;
+    explicit SetupPhase(std::string name);
+    ~SetupPhase();
+};
+// HNH_DEVICE_SETUP: "1" force the device-side setup path, "0" force the host path, unset: device when one is
+// present and the job is large enough to pay for the copies.
+bool device_setup_enabled(int64_t items);
+
 // Simple owning device array.
 template <typename T>
 class DeviceBuffer {

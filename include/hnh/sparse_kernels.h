@@ -64,6 +64,14 @@ public:
     bool values_are_zero = false;  // next sddmm_local may overwrite instead of accumulate
     bool output_is_zero = false;   // next spmm_local may overwrite instead of accumulate
     int flags = 0;                 // extra HNH_FLAG_* bits (testing)
+    // SDDMM epilogue (hnh_sddmm_scaled_f64): while sddmm_scale is set, sddmm_local multiplies the finished dot of
+    // nonzero i of block b by (*sddmm_scale)[S.blockStarts[b] + i] -- the reference's separate
+    // `SValues.cwiseProduct(getCSRValues())` pass (15D_dense_shift.hpp:364-368) -- and stores the product in
+    // *sddmm_scaled_out (same indexing) and, with sddmm_scale_values, in the block's CSR values as well.  Only legal
+    // when the call completes the dot (every block is met once per pass, as in the 1.5D dense-shift algorithm).
+    const VectorXd *sddmm_scale = nullptr;
+    VectorXd *sddmm_scaled_out = nullptr;
+    bool sddmm_scale_values = false;
 
     size_t sddmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B, int block, int offset) override;
     size_t spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B, MatMode mode, int block) override;

@@ -55,6 +55,8 @@ extern "C" {
 #define HNH_FLAG_TMA_STAGE 64
 /* experimental: per-warp TMA slots (no block barrier); never selected automatically */
 #define HNH_FLAG_TMA_WARP 128
+/* hnh_sddmm_scaled_f64 with scaled_out: the block's values receive scale * dot as well (default: the plain dot) */
+#define HNH_FLAG_SCALE_VALUES 256
 
 /* ABI / build identification. */
 int hnh_abi_version(void);
@@ -74,6 +76,15 @@ uint64_t hnh_launch_count(void);
 int hnh_sddmm_f64(const int64_t *rowStart, const int64_t *col_idx, double *values,
                   int64_t rows, int64_t nnz, const double *X, const double *Y, int r,
                   int flags, void *stream);
+/* The same with the Hadamard epilogue of the reference's `SValues.cwiseProduct(getCSRValues())`
+ * (15D_dense_shift.hpp:364-368, SpmatLocal.hpp:571-593) folded in: `scale` is aligned with `values`
+ * (scale[i] belongs to nonzero i of this block).  scaled_out != NULL: values[i] = dot (as above) and
+ * scaled_out[i] = scale[i] * dot.  scaled_out == NULL: values[i] = scale[i] * dot.  scale == NULL is
+ * hnh_sddmm_f64.  HNH_FLAG_SCALE_VALUES: with scaled_out, values[i] = scale[i] * dot too.  With accumulation
+ * (no BETA0) the old value is added to the dot BEFORE scaling. */
+int hnh_sddmm_scaled_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
+                         int64_t nnz, const double *X, const double *Y, int r, int flags, const double *scale,
+                         double *scaled_out, void *stream);
 
 /* Same operation driven by the expanded COO arrays the reference kernel actually reads
  * (`row_idx[i]`, `col_idx[i]`, sparse_kernels.cpp:45-47); needs no rowStart. */
@@ -164,6 +175,25 @@ int64_t hnh_er_generate_device(int logM, int nnz_per_row, uint64_t seed, int64_t
 int hnh_coo_to_csr_device(int64_t rows, int64_t cols, int64_t nnz, const uint64_t *r,
                           const uint64_t *c, const double *v, int transpose, int64_t *rowStart,
                           int64_t *col_idx, int64_t *row_idx, double *values, void *stream);
+
+/* Device-resident tuple pipeline of the setup path (SoA tuples r / c / v in HBM; reference: host vectors of
+ * spcoord_t, SpmatLocal.hpp:389-462).  All synchronise `stream` before returning; fewer than 2^31 tuples per call.
+ *  - bucket_by_owner: owner(i) = table[rb * table_cols + cb] with (rb, cb) = (r/rows_in_block, c/cols_in_block), or
+ *    (c/rows_in_block, r/cols_in_block) when `transpose` (NonzeroDistribution::getOwner, SpmatLocal.hpp:45-52); the
+ *    table is a HOST array filled from the distribution's blockOwner().  Output: the tuples grouped by owner in
+ *    input order (stable), r and c exchanged when `transpose`; starts_host[nbuckets + 1] = segment offsets.
+ *  - sort_colmajor: in place, ascending (c, r), ties in input order (the order redistribute_nonzeros leaves,
+ *    SpmatLocal.hpp:458).  max_r / max_c bound the keys (number of radix bits).
+ *  - mod: r %= mod_r, c %= mod_c (0 = leave).   - block_starts: first position with c >= k * block_width. */
+int hnh_tuples_bucket_by_owner_device(const uint64_t *r, const uint64_t *c, const double *v, int64_t n, int transpose,
+                                      int64_t rows_in_block, int64_t cols_in_block, const int *owner_table_host,
+                                      int64_t table_rows, int64_t table_cols, int nbuckets, uint64_t *r_out,
+                                      uint64_t *c_out, double *v_out, int64_t *starts_host, void *stream);
+int hnh_tuples_sort_colmajor_device(uint64_t *r, uint64_t *c, double *v, int64_t n, uint64_t max_r, uint64_t max_c,
+                                    void *stream);
+int hnh_tuples_mod_device(uint64_t *r, uint64_t *c, int64_t n, uint64_t mod_r, uint64_t mod_c, void *stream);
+int hnh_tuples_block_starts_device(const uint64_t *c_sorted, int64_t n, uint64_t block_width, int divisions,
+                                   int64_t *starts_host, void *stream);
 
 /* ---- host-buffer entry points (pinned or pageable HOST pointers) -------------------------
  * One call = H2D of the dense operands and values, the kernel(s), D2H of the results, all

@@ -92,6 +92,9 @@ int hnhd_alg_dims(hnhd_alg_t *alg, hnhd_alg_dims_t *out);
 int hnhd_alg_submatrices(hnhd_alg_t *alg, int which, int *out4, int capacity);
 /* JSON text of json_algorithm_info() / json_perf_statistics() (distributed_sparse.h:131-179,
  * 245-261).  Collective.  Returns the length written (excluding NUL) or a negative code. */
+/* Wall-clock seconds of the setup phases of this process so far (tuple generation, redistribution, COO -> CSR), as
+ * a JSON object {phase: seconds}; reset != 0 clears the counters afterwards. */
+int hnhd_setup_times_json(char *out, size_t capacity, int reset);
 int hnhd_alg_info_json(hnhd_alg_t *alg, char *out, size_t capacity);
 int hnhd_alg_perf_json(hnhd_alg_t *alg, char *out, size_t capacity);
 int hnhd_alg_reset_timers(hnhd_alg_t *alg);

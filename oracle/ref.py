@@ -194,9 +194,14 @@ def time_fused(alg, p, c, R, logM, nnz_per_row, seed, warmup, steps, threads_per
 def pattern(rows, cols, salt, row0=0, col0=0):
     """The position-dependent test operand of the parity legs (ref_driver.cpp::pattern_value): global rows
     [row0, row0 + rows) x columns [col0, col0 + cols).  Exactly representable in fp64."""
-    i = np.arange(row0, row0 + rows, dtype=np.uint64)[:, None]
+    return pattern_rows(np.arange(row0, row0 + rows, dtype=np.uint64), cols, salt, col0)
+
+
+def pattern_rows(row_index, cols, salt, col0=0):
+    """pattern() for an arbitrary list of global row indices."""
+    i = np.asarray(row_index, dtype=np.uint64)[:, None]
     k = np.arange(col0, col0 + cols, dtype=np.uint64)[None, :]
-    h = (i * np.uint64(2654435761) + k * np.uint64(40503) + np.uint64(salt * 97)) & np.uint64(0xFFFFFFFF)
+    h = (i * np.uint64(2654435761) + k * np.uint64(2246822519) + np.uint64(salt * 97)) & np.uint64(0xFFFFFFFF)
     return h.astype(np.float64) / 4294967296.0 - 0.5
 
 

@@ -292,7 +292,7 @@ struct TimeArgs { int logM, nnz_per_row, R, c, calls; const char *alg; double *s
 // Position-dependent test operand shared with bench.py's parity leg: exactly representable, so the CPU and the GPU
 // side start from bit-identical inputs.  salt 1 = A, salt 2 = B.
 static inline double pattern_value(uint64_t row, uint64_t col, uint64_t salt) {
-    const uint64_t h = (row * 2654435761ull + col * 40503ull + salt * 97ull) & 0xffffffffull;
+    const uint64_t h = (row * 2654435761ull + col * 2246822519ull + salt * 97ull) & 0xffffffffull;
     return (double)h / 4294967296.0 - 0.5;
 }
 static void time_main(int rank, void *arg) {

@@ -18,13 +18,13 @@ def free_port():
         return s.getsockname()[1]
 
 
-def run_cases(nproc, cases, transport, timeout=600):
-    """Returns {case name: [per-rank dict]}."""
+def run_cases(nproc, cases, transport, timeout=600, env_extra=None):
+    """Returns {case name: [per-rank dict]}.  env_extra: additional environment of the worker processes."""
     with tempfile.TemporaryDirectory() as td:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
                "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
                os.path.join(ROOT, "tests", "mp_worker.py"), json.dumps(cases), td, transport]
-        env = dict(os.environ, OMP_NUM_THREADS="2")
+        env = dict(os.environ, OMP_NUM_THREADS="2", **(env_extra or {}))
         p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout, text=True)
         if p.returncode != 0 and "Address already in use" in p.stdout:  # lost the race for the rendezvous port
             cmd[cmd.index("--master-port") + 1] = str(free_port())

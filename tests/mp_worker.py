@@ -209,6 +209,7 @@ def main():
             out["gat_out"] = net.buffer(len(layers))
             del net
         out["info"] = json.dumps(alg.info())
+        out["setup_times"] = json.dumps(D.setup_times(reset=True))
         np.savez(os.path.join(outdir, f"{name}_rank{rank}.npz"), **out)
         del alg, S
     D.world_finalize()  # also destroys the torch.distributed group (clean gloo teardown)

@@ -6,6 +6,7 @@ How the ranks are mapped: with at least `nproc` GPUs each rank gets its own GPU 
 shifts / collectives are NCCL; on a one-GPU box the ranks are processes sharing cuda:0 and the
 External transport (gloo, device buffers staged through pinned memory) carries the messages, so
 the algorithm code under test is identical."""
+import json
 import os
 
 import numpy as np
@@ -211,3 +212,36 @@ def test_null_and_empty_blocks_match_reference():
             U.compare_ops(got[c["name"]], want, c["script"])
         except AssertionError as e:
             raise AssertionError(f"case {c['name']} (reference from {src}): {e}") from e
+
+
+# Device-side setup: tuples generated, bucketed by owner, exchanged, sorted and turned into CSR blocks
+# in HBM.  Forced on for these small matrices (by default it starts at 2^18 tuples per rank); the per-rank layout must be
+# the reference's bit for bit, and every operation must still agree with it.
+DEVSETUP_CASES = {
+    1: [U.case("15d_fusion2", 1, 8, 7, 5), U.case("15d_fusion1", 1, 8, 7, 5), U.case("15d_sparse", 1, 8, 7, 5),
+        U.case("25d_dense_replicate", 1, 8, 7, 5), U.case("25d_sparse_replicate", 1, 8, 7, 5),
+        U.case("15d_sparse", 1, 16, 14, 8, name="cfg1_15d_sparse", load="er", script=["sddmmA", "fusedA"])],
+    2: CASES[2] + RECT_CASES[2],
+    4: CASES[4] + RECT_CASES[4] + TINY_CASES,
+}
+
+
+@pytest.mark.parametrize("nproc", [1, 2, 4])
+def test_device_side_setup_matches_reference(nproc):
+    from oracle import ref
+    cases = [dict(c, als=0) for c in DEVSETUP_CASES[nproc]]
+    got = U.run_cases(nproc, cases, transport_for(nproc) if nproc > 1 else "self", timeout=900, env_extra={"HNH_DEVICE_SETUP": "1"})
+    checked = 0
+    for c in cases:
+        want, src = U.reference_for(c, nproc)
+        if want is None:
+            continue
+        info = json.loads(str(got[c["name"]][0]["setup_times"]))
+        assert any("(device)" in k for k in info), (c["name"], "the device setup path did not run", info)
+        try:
+            U.compare_layout(got[c["name"]], want, c["alg"])
+            U.compare_ops(got[c["name"]], want, c["script"])
+        except AssertionError as e:
+            raise AssertionError(f"case {c['name']} (p={nproc}, device setup, reference from {src}): {e}") from e
+        checked += 1
+    assert checked > 0
