@@ -50,6 +50,10 @@ ABI = {
     "hnh_spmm_host": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _I64, _P, C.c_int]),
     "hnh_er_generate_device": (C.c_int64, [C.c_int, C.c_int, C.c_uint64, _I64, _I64, _P, _P, _P, _I64, _P]),
     "hnh_coo_to_csr_device": (C.c_int, [_I64, _I64, _I64, _P, _P, _P, C.c_int, _P, _P, _P, _P, _P]),
+    "hnh_tuples_bucket_by_owner_device": (C.c_int, [_P, _P, _P, _I64, C.c_int, _I64, _I64, _P, _I64, _I64, C.c_int, _P, _P, _P, _P, _P]),
+    "hnh_tuples_sort_colmajor_device": (C.c_int, [_P, _P, _P, _I64, C.c_uint64, C.c_uint64, _P]),
+    "hnh_tuples_mod_device": (C.c_int, [_P, _P, _I64, C.c_uint64, C.c_uint64, _P]),
+    "hnh_tuples_block_starts_device": (C.c_int, [_P, _I64, C.c_uint64, C.c_int, _P, _P]),
 }
 
 
