@@ -262,64 +262,96 @@ def run_reference_arm(args):
 PARITY_RTOL = 1e-5  # BASELINE.json north_star: fp64 values within 1e-5 relative
 
 
-def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
-    """One fusedSpMM on position-dependent operands (oracle/ref.py::pattern, exactly representable) at the FULL
-    benchmark size, on the data plane that was just timed (same algorithm object, same rings), checked two ways:
-      sample: `rows_per_rank` consecutive output rows of every rank against the C port of the reference kernels
-              (oracle/hnh_oracle.c, pinned bit-exact to the reference's loop) on the same tuples;
-      full  : every output row against one fusedSpMM of the reference's own code (oracle/_ref, p = 1) -- computed on
-              rank 0 and handed to the ranks over gloo.
-    Returns the `parity_check` object of the JSON line; never raises (a failure is reported, not hidden)."""
+def pattern_local(subs, shape, salt, nrows_global):
+    """This rank's shard of the global pattern operand: the submatrix blocks (top, left, rows, cols) stacked in local
+    storage order (DenseSubmatrix descriptors, distributed_sparse.h:322-346); rows beyond the matrix are zero."""
+    from oracle import ref
+    flat = np.zeros(shape[0] * shape[1])
+    at = 0
+    for top, left, nr, nc in subs:
+        blk = ref.pattern(int(nr), int(nc), salt, row0=int(top), col0=int(left))
+        blk[max(0, nrows_global - int(top)):] = 0.0
+        flat[at:at + nr * nc] = blk.reshape(-1)
+        at += nr * nc
+    return flat.reshape(shape)
+
+
+def sample_parity(logM, npr, R, alg, A, B, Sv, res, rank, world, shifts=False, rows_per_block=2048):
+    """FusedMM (mode A) of `alg` on the pattern operands; `rows_per_block` consecutive rows of every local submatrix
+    block are compared with the C port of the reference kernels (oracle/hnh_oracle.c: SDDMM over the full width, then
+    SpMM) on the same tuples -- for any layout, R-split ones included.  Returns (this rank's output, stats dict)."""
     import torch
     import torch.distributed as dist
     from distributed_sddmm_b200 import lib
     from oracle import hnh_oracle as orc
     from oracle import ref
     L = lib()
-    out = {"tolerance": PARITY_RTOL, "inputs": "A = pattern(1), B = pattern(2) (oracle/ref.py), S pattern all ones"}
-    try:
-        N, R = 1 << args.logM, args.R
-        (topA, leftA, nrA, ncA), (topB, leftB, nrB, ncB) = alg.submatrices("A")[0], alg.submatrices("B")[0]
-        hA = ref.pattern(nrA, ncA, 1, row0=topA, col0=leftA)
-        hB = ref.pattern(nrB, ncB, 2, row0=topB, col0=leftB)
-        hA[max(0, N - topA):] = 0.0  # padding rows beyond the matrix (none when p divides N)
-        hB[max(0, N - topB):] = 0.0
-        A.from_host(hA)
-        B.from_host(hB)
-        alg.fusedSpMM(A, B, Sv, res, "A")
-        got = A.to_host()
-        A.fill(0.001)
-        B.fill(0.001)
-        live = max(0, min(nrA, N - topA))
-
-        # ---- sample: the C port on this rank's rows [lo, hi) ----
-        n_s = min(live, 2048)
-        lo = topA + (live - n_s) // 3
-        cap = n_s * args.nnz_per_row
+    N = 1 << logM
+    subsA, subsB = alg.submatrices("A"), alg.submatrices("B")
+    shapeA, shapeB = A.shape, B.shape
+    A.from_host(pattern_local(subsA, shapeA, 1, N))
+    B.from_host(pattern_local(subsB, shapeB, 2, N))
+    if shifts:
+        alg.initial_shift(A, B, "sddmmA")
+    alg.fusedSpMM(A, B, Sv, res, "A")
+    if shifts:
+        alg.de_shift(A, B, "sddmmA")
+    got = A.to_host()
+    flat = got.reshape(-1)
+    err, rows_checked, nnz_checked, at = 0.0, 0, 0, 0
+    for top, left, nr, nc in subsA:
+        top, left, nr, nc = int(top), int(left), int(nr), int(nc)
+        blk = flat[at:at + nr * nc].reshape(nr, nc)
+        at += nr * nc
+        live = max(0, min(nr, N - top))
+        n_s = min(live, rows_per_block)
+        if n_s == 0:
+            continue
+        lo = top + (live - n_s) // 3
+        cap = n_s * npr
         r_, c_, v_ = np.empty(cap, np.uint64), np.empty(cap, np.uint64), np.empty(cap, np.float64)
-        n = L.hnh_er_generate_host(args.logM, args.nnz_per_row, SEED, lo, lo + n_s, r_.ctypes.data, c_.ctypes.data,
-                                   v_.ctypes.data, cap)
+        n = L.hnh_er_generate_host(logM, npr, SEED, lo, lo + n_s, r_.ctypes.data, c_.ctypes.data, v_.ctypes.data, cap)
         r_, c_, v_ = r_[:n], c_[:n], v_[:n]
         ucols, inv = np.unique(c_, return_inverse=True)
         csr = orc.coo_to_csr(n_s, len(ucols), r_ - np.uint64(lo), inv.astype(np.uint64), v_)
-        Bs = ref.pattern_rows(ucols, R, 2)
-        As = ref.pattern(n_s, R, 1, row0=lo)
         want = np.zeros((n_s, R))
-        orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), As, Bs, want)
-        have = got[lo - topA:lo - topA + n_s]
-        scale = max(float(np.abs(want).max()), 1e-300)
-        err_s = float(np.abs(have - want).max() / scale)
-        stats = torch.tensor([err_s, float(n_s), float(n)], dtype=torch.float64)
-        if world > 1:
-            worst = stats.clone()
-            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-            tot = stats.clone()
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            err_s, rows_s, nnz_s = float(worst[0]), int(tot[1]), int(tot[2])
-        else:
-            rows_s, nnz_s = n_s, n
-        out["sample"] = {"checker": "oracle/hnh_oracle.c (C port of sparse_kernels.cpp:44-55 + CSR SpMM), same tuples",
-                         "rows": rows_s, "nnz": nnz_s, "max_rel_err": err_s}
+        orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), ref.pattern(n_s, R, 1, row0=lo),
+                        ref.pattern_rows(ucols, R, 2), want)
+        want = want[:, left:left + nc]
+        have = blk[lo - top:lo - top + n_s]
+        err = max(err, float(np.abs(have - want).max() / max(float(np.abs(want).max()), 1e-300)))
+        rows_checked += n_s
+        nnz_checked += int(n)
+    stats = torch.tensor([err, float(rows_checked), float(nnz_checked)], dtype=torch.float64)
+    if world > 1:
+        worst, tot = stats.clone(), stats.clone()
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        err, rows_checked, nnz_checked = float(worst[0]), int(tot[1]), int(tot[2])
+    return got, {"checker": "oracle/hnh_oracle.c (C port of sparse_kernels.cpp:44-55 + CSR SpMM), same tuples",
+                 "rows": rows_checked, "nnz": nnz_checked, "max_rel_err": err}
+
+
+def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
+    """One fusedSpMM on position-dependent operands (oracle/ref.py::pattern, exactly representable) at the FULL
+    benchmark size, on the data plane that was just timed (same algorithm object, same rings), checked two ways:
+      sample: consecutive output rows of every rank against the C port of the reference kernels
+              (oracle/hnh_oracle.c, pinned bit-exact to the reference's loop) on the same tuples;
+      full  : every output row against one fusedSpMM of the reference's own code (oracle/_ref, p = 1) -- computed on
+              rank 0 and handed to the ranks over gloo.
+    Returns the `parity_check` object of the JSON line; never raises (a failure is reported, not hidden)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import ref
+    out = {"tolerance": PARITY_RTOL, "inputs": "A = pattern(1), B = pattern(2) (oracle/ref.py), S pattern all ones"}
+    try:
+        N, R = 1 << args.logM, args.R
+        topA, leftA, nrA, ncA = (int(x) for x in alg.submatrices("A")[0])
+        got, out["sample"] = sample_parity(args.logM, args.nnz_per_row, R, alg, A, B, Sv, res, rank, world)
+        A.fill(0.001)
+        B.fill(0.001)
+        live = max(0, min(nrA, N - topA))
+        rows_s = out["sample"]["rows"]
 
         # ---- full: the reference's own fusedSpMM ----
         if want_full:

@@ -2,14 +2,10 @@
 // gat.hpp:84-113) needs beyond the SDDMM / SpMM path: LeakyReLU on an edge-value vector, ReLU of a head's
 // output written into its column window of the layer output, and the dense projection X * W.
 //
-// The projection is a plain fp64 library GEMM: cuBLAS (DMMA tensor-core path), bound at first use with
-// dlopen so that libhnh_b200.so carries no load-time dependency on libcublas -- everything except
-// hnh_dgemm_f64 works without it.
-#include <cublas_v2.h>
-#include <dlfcn.h>
-
+// The projection is this library's own fp64 GEMM (dgemm_dmma_kernel below): C = A B for a tall A (rows of the
+// graph) and a small B (the head's weight matrix), on the fp64 tensor-core path (mma.sync m8n8k4, DMMA) with
+// shared-memory tiles.  Blackwell's tcgen05 has no fp64 kind, so mma.sync IS the fp64 tensor path on sm_100a.
 #include <algorithm>
-#include <mutex>
 
 #include "hnh_b200.h"
 #include "launch.h"
@@ -51,39 +47,74 @@ int grid_for_elements(int64_t n, int *grid) {
     return HNH_OK;
 }
 
-// ---- cuBLAS, bound lazily -----------------------------------------------------------------------
-struct Cublas {
-    void *lib = nullptr;
-    cublasHandle_t handle = nullptr;
-    cublasStatus_t (*create)(cublasHandle_t *) = nullptr;
-    cublasStatus_t (*set_stream)(cublasHandle_t, cudaStream_t) = nullptr;
-    cublasStatus_t (*dgemm)(cublasHandle_t, cublasOperation_t, cublasOperation_t, int, int, int, const double *, const double *,
-                            int, const double *, int, const double *, double *, int) = nullptr;
-    bool failed = false;
-};
-Cublas g_blas;
-std::mutex g_blas_mu;
+// ---- fp64 GEMM on DMMA ---------------------------------------------------------------------------------
+// C (m x n) = A (m x k) B (k x n), all row-major, contiguous.  CTA tile 64 x 64, 4 warps of 32 x 32 (4 x 4 DMMA tiles
+// of 8 x 8), K in steps of 16 through shared memory.  Fragment layout of mma.m8n8k4.f64 (PTX ISA): with g = lane / 4,
+// t = lane % 4:  A[g][t],  B[t][g],  C[g][2t], C[g][2t + 1].  The shared-memory row strides (20 and 68 doubles) put
+// the 16 lanes of a half-warp on 16 different bank pairs for both fragment loads.  Edges are zero-filled on load and
+// masked on store, so any m, n, k >= 1 works.
+constexpr int GM = 64, GN = 64, GK = 16, GA_LD = GK + 4, GB_LD = GN + 4;
 
-int bind_cublas() {
-    if (g_blas.handle) return HNH_OK;
-    if (g_blas.failed) return set_error(HNH_E_INVALID, "hnh_dgemm_f64: cuBLAS is not available in this process");
-    g_blas.failed = true;
-    for (const char *name : {"libcublas.so.12", "libcublas.so"}) {
-        g_blas.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
-        if (g_blas.lib) break;
+__device__ __forceinline__ void dmma_8x8x4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128)
+dgemm_dmma_kernel(double *__restrict__ C, const double *__restrict__ A, const double *__restrict__ B, int64_t m, int n, int k) {
+    __shared__ double As[GM][GA_LD];
+    __shared__ double Bs[GK][GB_LD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;  // this warp's 32 x 32 corner inside the CTA tile
+    const int col_tiles = (n + GN - 1) / GN;
+    const int64_t row_tiles = (m + GM - 1) / GM;
+    for (int64_t tile = blockIdx.x; tile < row_tiles * col_tiles; tile += gridDim.x) {
+        const int64_t row0 = (tile / col_tiles) * GM;
+        const int col0 = (int)(tile % col_tiles) * GN;
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int k0 = 0; k0 < k; k0 += GK) {
+            __syncthreads();  // the previous K step has been consumed
+            for (int e = threadIdx.x; e < GM * GK; e += 128) {
+                const int r = e / GK, c = e % GK;
+                const int64_t gr = row0 + r;
+                As[r][c] = (gr < m && k0 + c < k) ? A[gr * k + k0 + c] : 0.0;
+            }
+            for (int e = threadIdx.x; e < GK * GN; e += 128) {
+                const int r = e / GN, c = e % GN;
+                Bs[r][c] = (k0 + r < k && col0 + c < n) ? B[(int64_t)(k0 + r) * n + col0 + c] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < GK; kk += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) a[i] = As[wr + i * 8 + g][kk + t];
+#pragma unroll
+                for (int j = 0; j < 4; j++) b[j] = Bs[kk + t][wc + j * 8 + g];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int64_t r = row0 + wr + i * 8 + g;
+            if (r >= m) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = col0 + wc + j * 8 + 2 * t;
+                if (c < n) C[r * n + c] = acc[i][j][0];
+                if (c + 1 < n) C[r * n + c + 1] = acc[i][j][1];
+            }
+        }
     }
-    if (!g_blas.lib) return set_error(HNH_E_INVALID, "hnh_dgemm_f64: cannot load libcublas.so.12 (%s)", dlerror());
-    g_blas.create = (decltype(g_blas.create))dlsym(g_blas.lib, "cublasCreate_v2");
-    g_blas.set_stream = (decltype(g_blas.set_stream))dlsym(g_blas.lib, "cublasSetStream_v2");
-    g_blas.dgemm = (decltype(g_blas.dgemm))dlsym(g_blas.lib, "cublasDgemm_v2");
-    if (!g_blas.create || !g_blas.set_stream || !g_blas.dgemm)
-        return set_error(HNH_E_INVALID, "hnh_dgemm_f64: libcublas lacks cublasCreate_v2 / cublasSetStream_v2 / cublasDgemm_v2");
-    cublasHandle_t h = nullptr;
-    const cublasStatus_t st = g_blas.create(&h);
-    if (st != CUBLAS_STATUS_SUCCESS) return set_error(HNH_E_CUDA, "hnh_dgemm_f64: cublasCreate failed (status %d)", (int)st);
-    g_blas.handle = h;
-    g_blas.failed = false;
-    return HNH_OK;
 }
 
 }  // namespace
@@ -123,15 +154,14 @@ int hnh_dgemm_f64(double *C, const double *A, const double *B, int64_t m, int64_
     if (!C || (k > 0 && (!A || !B))) return set_error(HNH_E_INVALID, "hnh_dgemm_f64: null pointer");
     if (k == 0)
         return check_cuda(cudaMemsetAsync(C, 0, sizeof(double) * (size_t)(m * n), (cudaStream_t)stream), "cudaMemsetAsync");
-    std::lock_guard<std::mutex> lk(g_blas_mu);
-    int rc = bind_cublas();
+    int sms = 0;
+    int rc = hnh::device_sm_count(&sms);
     if (rc) return rc;
-    cublasStatus_t st = g_blas.set_stream(g_blas.handle, (cudaStream_t)stream);
-    if (st != CUBLAS_STATUS_SUCCESS) return set_error(HNH_E_CUDA, "hnh_dgemm_f64: cublasSetStream failed (status %d)", (int)st);
-    // row-major C (m x n) = A (m x k) B (k x n)  <=>  column-major C^T (n x m) = B^T (n x k) A^T (k x m)
-    const double one = 1.0, zero = 0.0;
-    st = g_blas.dgemm(g_blas.handle, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)m, (int)k, &one, B, (int)n, A, (int)k, &zero, C, (int)n);
-    if (st != CUBLAS_STATUS_SUCCESS) return set_error(HNH_E_CUDA, "hnh_dgemm_f64: cublasDgemm failed (status %d)", (int)st);
+    const int64_t tiles = ((m + GM - 1) / GM) * ((n + GN - 1) / GN);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sms * 8));
+    dgemm_dmma_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(C, A, B, m, (int)n, (int)k);
+    rc = check_cuda(cudaGetLastError(), "dgemm_dmma_kernel launch");
+    if (rc) return rc;
     count_launch(1);
     return HNH_OK;
 }

@@ -142,7 +142,7 @@ public:
     DenseMatrix cwiseProduct(const DenseMatrix &o) const;
     double squaredNorm() const;
 
-    // matrix product (gat.hpp:90 `buffers[i] * wMats[j]`): cuBLAS DGEMM on the compute stream
+    // matrix product (gat.hpp:90 `buffers[i] * wMats[j]`): this library's DMMA GEMM (hnh_dgemm_f64) on the compute stream
     DenseMatrix operator*(const DenseMatrix &o) const;
     // this.middleCols(start, m.cols()) = m.array().max(0)   (gat.hpp:104)
     void setMiddleColsRelu(int64_t start, const DenseMatrix &m);

@@ -4,7 +4,7 @@
 // forwardPass}: gat.hpp:26-113; used at benchmark_dist.cpp:88-94,133-135) so that its callers compile.
 //
 // One head of one layer:
-//     H      = X_in * W                       dense projection          (cuBLAS DGEMM, hnh_dgemm_f64)
+//     H      = X_in * W                       dense projection          (hnh_dgemm_f64: own fp64 DMMA kernel)
 //     e_uv   = <H_u, H_v> for every edge      SDDMM through d_ops       (K1)
 //     e_uv   = LeakyReLU(e_uv)                                           (hnh_leaky_relu_f64)
 //     Z      = E * H                          SpMM through d_ops        (K2)

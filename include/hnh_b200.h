@@ -146,7 +146,7 @@ int hnh_leaky_relu_f64(double *dst, const double *src, int64_t n, double alpha, 
 int hnh_relu_cols_f64(double *dst, int64_t ld_dst, int64_t col0, const double *src, int64_t rows,
                       int64_t cols, void *stream);
 /* C (m x n) = A (m x k) * B (k x n), all row-major and contiguous (buffers[i] * wMats[j],
- * gat.hpp:90).  A plain library GEMM: cuBLAS, loaded on first use. */
+ * gat.hpp:90).  This library's own kernel: fp64 tensor-core MMA (mma.sync m8n8k4) over shared-memory tiles. */
 int hnh_dgemm_f64(double *C, const double *A, const double *B, int64_t m, int64_t n, int64_t k,
                   void *stream);
 

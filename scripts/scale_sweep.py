@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from bench import SEED, fusedmm_bytes_per_rank  # noqa: E402
+from bench import PARITY_RTOL, SEED, fusedmm_bytes_per_rank, sample_parity  # noqa: E402
 from distributed_sddmm_b200 import driver as D  # noqa: E402
 from distributed_sddmm_b200 import lib  # noqa: E402
 
@@ -65,11 +65,22 @@ for name in algs:
         L.hnhd_device_synchronize(); L.hnhd_barrier()
         perf = alg.perf()
         info = alg.info()
+        # correctness of the data plane just timed, at this size (row samples of every rank against the C port of the
+        # reference kernels; Cannon layouts need the alignment shifts the benchmark loop leaves out)
+        parity = None
+        if os.environ.get("PARITY", "1") != "0":
+            try:
+                _, parity = sample_parity(logM, npr, R, alg, A, B, Sv, res, rank, world, shifts=name.startswith("25d"),
+                                          rows_per_block=int(os.environ.get("PARITY_ROWS", "1024")))
+                parity["pass"] = bool(parity["max_rel_err"] <= PARITY_RTOL)
+            except Exception as e:  # noqa: BLE001
+                parity = {"error": f"{type(e).__name__}: {e}", "pass": False}
         if rank == 0:
             rec = {"alg": name, "p": world, "c": c, "R": R, "logM": logM, "ms_per_fusedmm": ms,
                    "gflops": 4.0 * nnz * R / ms / 1e6,
                    "phase_ms": {k: v * 1e3 / steps for k, v in perf.items()},
-                   "nnz_max_over_ranks": max(info["nnz_procs"]), "nnz_mean": float(np.mean(info["nnz_procs"]))}
+                   "nnz_max_over_ranks": max(info["nnz_procs"]), "nnz_mean": float(np.mean(info["nnz_procs"])),
+                   "ring": info.get("ring"), "parity_check": parity, "setup_s": D.setup_times(reset=True)}
             if name in ("15d_fusion1", "15d_fusion2"):
                 by = fusedmm_bytes_per_rank(name, rec["nnz_mean"], alg.dims.localArows * c, world // c, R)
                 rec["kernel_GBps_per_gpu"] = by / (rec["phase_ms"]["Computation Time"] * 1e-3) / 1e9

@@ -143,8 +143,12 @@ def main():
                 coords[which] = got
                 out[which + "_rows"], out[which + "_cols"] = got
             Sv, STv = alg.like_S_values(0.0), alg.like_ST_values(0.0)
-            Sv.from_host(sval(*coords["S"]))
-            STv.from_host(sval(*coords["ST"]))
+            if case.get("load", "tuples") == "er":  # generator path: every nonzero is 1.0
+                Sv.fill(1.0)
+                STv.fill(1.0)
+            else:
+                Sv.from_host(sval(*coords["S"]))
+                STv.from_host(sval(*coords["ST"]))
             res_s, res_st = alg.like_S_values(0.0), alg.like_ST_values(0.0)
             for t, op in enumerate(script):
                 A.from_host(gather_local(GA, subsA, shapeA))

@@ -191,12 +191,15 @@ def test_gat_device_helpers(world):
     want[:, 10:15] = np.maximum(src, 0)
     assert np.array_equal(ddst.cpu().numpy(), want)
     assert L.hnh_relu_cols_f64(ddst.data_ptr(), 17, 13, dsrc.data_ptr(), 33, 5, st) == -1  # window past the row end
-    A, B = rng.uniform(-1, 1, (70, 19)), rng.uniform(-1, 1, (19, 11))
-    dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
-    dC = torch.empty((70, 11), dtype=torch.float64, device=dev)
-    D.check(L.hnh_dgemm_f64(dC.data_ptr(), dA.data_ptr(), dB.data_ptr(), 70, 11, 19, st))
-    torch.cuda.synchronize()
-    assert rel_err(dC.cpu().numpy(), A @ B) < 1e-13
+    # the library's own fp64 tensor-core GEMM (dgemm_dmma_kernel): ragged edges, several K steps, several column tiles,
+    # more row tiles than CTAs
+    for m, n, k in ((70, 11, 19), (1, 1, 1), (64, 64, 16), (300, 130, 37), (5, 200, 3), (100000, 32, 256)):
+        A, B = rng.uniform(-1, 1, (m, k)), rng.uniform(-1, 1, (k, n))
+        dA, dB = torch.from_numpy(A).to(dev), torch.from_numpy(B).to(dev)
+        dC = torch.full((m, n), float("nan"), dtype=torch.float64, device=dev)
+        D.check(L.hnh_dgemm_f64(dC.data_ptr(), dA.data_ptr(), dB.data_ptr(), m, n, k, st))
+        torch.cuda.synchronize()
+        assert rel_err(dC.cpu().numpy(), A @ B) < 1e-13, (m, n, k)
 
 
 @pytest.mark.parametrize("name", ALGS)
