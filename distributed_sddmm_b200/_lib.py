@@ -29,6 +29,7 @@ ABI = {
     "hnh_sddmm_coo_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_spmm_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, C.c_int, C.c_int, _P]),
     "hnh_fused_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "hnh_fused_scaled_f64": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "hnh_fill_f64": (C.c_int, [_P, _I64, C.c_double, _P]),
     "hnh_random_uniform_f64": (C.c_int, [_P, _I64, C.c_uint64, _P]),
     "hnh_hadamard_f64": (C.c_int, [_P, _P, _P, _I64, _P]),

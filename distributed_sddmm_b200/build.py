@@ -95,6 +95,13 @@ def build_reference_driver() -> str | None:
         _compile_reference_main(src, "bench_er_reference_harness", extra=["/root/reference/benchmark_dist.cpp"])
     except subprocess.CalledProcessError as e:
         sys.stderr.write(f"build: the reference's benchmark_dist.cpp did not compile against include/hnh/compat ({e})\n")
+    # the reference's ALS (als_conjugate_gradients.cpp, unchanged: Eigen expressions, the host loop of scale_matrix_rows,
+    # raw MPI_Allreduce) under this repo's small driver, on this library's classes (host-access mode, hnh/runtime.h)
+    try:
+        _compile_reference_main(os.path.join(HERE, "tools", "als_reference_main.cpp"), "als_reference_main",
+                                extra=["/root/reference/als_conjugate_gradients.cpp"])
+    except subprocess.CalledProcessError as e:
+        sys.stderr.write(f"build: the reference's als_conjugate_gradients.cpp did not compile against include/hnh/compat ({e})\n")
     return exe
 
 

@@ -183,6 +183,20 @@ void hnh_world_init_from_env() {
     if (rank == 0) unlink(path);
 }
 
+void hnh_compat_allreduce_sum_f64(double *buf, size_t count, hnh::Comm &comm) {
+    cudaPointerAttributes attr;
+    const bool device_side = hnh::Runtime::get().has_device() && cudaPointerGetAttributes(&attr, buf) == cudaSuccess &&
+                             (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    if (!device_side) {
+        cudaGetLastError();
+        comm.host_allreduce_sum_f64(buf, count);
+        return;
+    }
+    cudaStream_t s = hnh::Runtime::get().compute_stream();
+    comm.allreduce_sum_f64(buf, count, s);
+    hnh::cuda_check(cudaStreamSynchronize(s), "MPI_Allreduce stand-in");
+}
+
 void hnh_world_finalize() {
     if (hnh::Runtime::get().has_device()) hnh::Runtime::get().sync_all();
     hnh::Comm::finalize();

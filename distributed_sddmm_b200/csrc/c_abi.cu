@@ -105,13 +105,16 @@ int launch_spmm(const int64_t *rowStart, const int64_t *col_idx, const double *v
 }
 template <int R, int G, int VW, int UN>
 int launch_fused(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
-                 const double *X, const double *Y, double *Out, bool bv, bool bo, cudaStream_t st) {
+                 const double *X, const double *Y, double *Out, bool bv, bool bo, cudaStream_t st,
+                 const double *scale = nullptr, double *scaled_out = nullptr) {
     int grid;
     auto k = bv ? (bo ? fused_row_kernel<R, G, VW, UN, true, true> : fused_row_kernel<R, G, VW, UN, true, false>)
                 : (bo ? fused_row_kernel<R, G, VW, UN, false, true> : fused_row_kernel<R, G, VW, UN, false, false>);
+    if (scale)  // scaled epilogue: first-visit form only (hnh_fused_scaled_f64 checks)
+        k = bo ? fused_row_kernel<R, G, VW, UN, true, true, true> : fused_row_kernel<R, G, VW, UN, true, false, true>;
     int rc = grid_for(k, kBlock, kBlock / G, rows, &grid);
     if (rc) return rc;
-    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out, scale, scaled_out);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "fused_row_kernel launch");
 }
@@ -154,13 +157,15 @@ int launch_spmm_split(const int64_t *rowStart, const int64_t *col_idx, const dou
 template <int R, int GK, int GN, int VW, int UN>
 int launch_fused_split(const int64_t *rowStart, const int64_t *col_idx, double *values,
                        int64_t rows, const double *X, const double *Y, double *Out, bool bv, bool bo,
-                       cudaStream_t st) {
+                       cudaStream_t st, const double *scale = nullptr, double *scaled_out = nullptr) {
     int grid;
     auto k = bv ? (bo ? fused_split_kernel<R, GK, GN, VW, UN, true, true> : fused_split_kernel<R, GK, GN, VW, UN, true, false>)
                 : (bo ? fused_split_kernel<R, GK, GN, VW, UN, false, true> : fused_split_kernel<R, GK, GN, VW, UN, false, false>);
+    if (scale)
+        k = bo ? fused_split_kernel<R, GK, GN, VW, UN, true, true, true> : fused_split_kernel<R, GK, GN, VW, UN, true, false, true>;
     int rc = grid_for(k, kBlock, kBlock / (GK * GN), rows, &grid);
     if (rc) return rc;
-    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out);
+    k<<<grid, kBlock, 0, st>>>(rowStart, col_idx, values, rows, X, Y, Out, scale, scaled_out);
     count_launch(1);
     return check_cuda(cudaGetLastError(), "fused_split_kernel launch");
 }
@@ -421,10 +426,11 @@ int hnh_spmm_f64(const int64_t *rowStart, const int64_t *col_idx, const double *
     return rc;
 }
 
-int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
-                  int64_t nnz, const double *X, const double *Y, double *Out, int r, int flags,
-                  void *stream) {
+int hnh_fused_scaled_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
+                         int64_t nnz, const double *X, const double *Y, double *Out, int r, int flags,
+                         const double *scale, double *scaled_out, void *stream) {
     int v = validate_common(rowStart, col_idx, values, rows, nnz, r, "hnh_fused_f64");
+    if (scaled_out && !scale) return set_error(HNH_E_INVALID, "hnh_fused_scaled_f64: scaled_out without scale");
     if (v < 0) return v;
     cudaStream_t st = (cudaStream_t)stream;
     if (v == 1) {
@@ -444,7 +450,7 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
     const bool a16 = aligned(X, 16) && aligned(Y, 16) && aligned(Out, 16);
     const bool a32 = aligned(X, 32) && aligned(Y, 32) && aligned(Out, 32);
 #define S4(R, G, VW, UN) \
-    rc = launch_fused<R, G, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)
+    rc = launch_fused<R, G, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st, scale, scaled_out)
 #define SGEN                                                                                 \
     {                                                                                        \
         int grid;                                                                            \
@@ -457,6 +463,16 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         }                                                                                    \
     }
     const bool table_r = r == 4 || r == 8 || r == 16 || r == 32 || r == 64 || r == 128 || r == 256;
+    if (scale) {
+        // the scaled epilogue exists in the first-visit form of the direct-load table kernels only
+        if (!bv) return set_error(HNH_E_INVALID, "hnh_fused_scaled_f64: scale needs HNH_FLAG_BETA0_VALUES");
+        if (!a16 || !table_r || (flags & HNH_FLAG_FORCE_GENERIC))
+            return set_error(HNH_E_INVALID, "hnh_fused_scaled_f64: scale needs a table width (4..256, power of two) and 16-byte "
+                                            "aligned operands");
+        if (values == scale || (const double *)scaled_out == scale)
+            return set_error(HNH_E_INVALID, "hnh_fused_scaled_f64: scale must not alias values / scaled_out");
+        flags = (flags | HNH_FLAG_FORCE_DIRECT) & ~(HNH_FLAG_TMA_STAGE | HNH_FLAG_TMA_WARP);
+    }
     // in place (Out == X) is not offered with TMA staging: the next tile of X is prefetched while
     // the current one is still being written
     if ((flags & HNH_FLAG_TMA_WARP) && a32 && (r == 128 || r == 256) && X != Out && !(flags & HNH_FLAG_FORCE_GENERIC)) {
@@ -478,7 +494,7 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
         SGEN
     } else if (r <= split_max_r() && r <= 32) {
 #define SP(R, GK, GN, VW, UN) \
-    rc = launch_fused_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st)
+    rc = launch_fused_split<R, GK, GN, VW, UN>(rowStart, col_idx, values, rows, X, Y, Out, bv, bo, st, scale, scaled_out)
         HNH_DISPATCH_SPLIT(r, a32, SP)
 #undef SP
     } else {
@@ -487,6 +503,12 @@ int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *value
 #undef S4
 #undef SGEN
     return rc;
+}
+
+int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
+                  int64_t nnz, const double *X, const double *Y, double *Out, int r, int flags,
+                  void *stream) {
+    return hnh_fused_scaled_f64(rowStart, col_idx, values, rows, nnz, X, Y, Out, r, flags, nullptr, nullptr, stream);
 }
 
 // ---- K4 + row algebra -----------------------------------------------------------------------

@@ -52,6 +52,13 @@ VectorXd VectorXd::Constant(int64_t n, double value) {
     return v;
 }
 void VectorXd::setConstant(double v) { abi_check(hnh_fill_f64(data(), n_, v, cs()), "fill"); }
+double &VectorXd::operator[](int64_t i) {
+    if (!hnh::Runtime::managed_mode())
+        throw hnh::Error(HNH_E_INVALID, "VectorXd::operator[]: element access from the host needs host-access mode "
+                                        "(HNH_MANAGED_MEMORY=1 / the compat <Eigen/Dense>); the vector lives in HBM");
+    if (i < 0 || i >= n_) throw hnh::Error(HNH_E_INVALID, "VectorXd::operator[]: index out of range");
+    return data()[i];
+}
 VectorXd VectorXd::cwiseProduct(const VectorXd &o) const {
     require(o.n_ == n_, "cwiseProduct: size mismatch");
     VectorXd r(n_);
@@ -177,11 +184,25 @@ DenseMatrix DenseMatrix::operator-(const DenseMatrix &o) const {
     r -= o;
     return r;
 }
-DenseMatrix DenseMatrix::cwiseProduct(const DenseMatrix &o) const {
-    require(o.size() == size(), "cwiseProduct: shape mismatch");
-    DenseMatrix r(rows_, cols_);
-    abi_check(hnh_hadamard_f64(r.data(), data(), o.data(), size(), cs()), "hadamard");
+DenseMatrix::CwiseProduct DenseMatrix::cwiseProduct(const DenseMatrix &o) const {
+    require(o.rows() == rows_ && o.cols() == cols_, "cwiseProduct: shape mismatch");
+    return CwiseProduct{*this, o};
+}
+DenseMatrix::CwiseProduct::operator DenseMatrix() const {
+    DenseMatrix r(a.rows(), a.cols());
+    abi_check(hnh_hadamard_f64(r.data(), a.data(), b.data(), a.size(), cs()), "hadamard");
     return r;
+}
+VectorXd DenseMatrix::CwiseProduct::Rowwise::sum() const { return batch_dot_product(a, b); }
+DenseMatrix operator*(double s, const DenseMatrix &m) {
+    DenseMatrix r(m);
+    r *= s;
+    return r;
+}
+void DenseMatrix::setRandom() {
+    // Eigen's setRandom() draws from the C library generator; here: the next seed of a fixed per-process sequence
+    static uint64_t next = 0x5EED0000ull;
+    setRandom(next++);
 }
 double DenseMatrix::squaredNorm() const {
     hnh::DeviceBuffer<double> out(1);

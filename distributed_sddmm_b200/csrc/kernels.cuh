@@ -262,11 +262,14 @@ spmm_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict_
 // values[j] += X[row].Y[col_j];  Out[row] += sum_j values[j] * Y[col_j]; one gather per nnz.
 // BV: values = dot (old values not read).  BO: Out = result (old Out not read); Out may then
 // alias X (each row of X is read only by the group that later writes that row of Out).
-template <int R, int G, int VW, int UN, bool BV, bool BO>
+// SC: values[j] = scale[j] * (X[row].Y[col_j]) -- the reference's Hadamard product with the caller's S values between
+// its SDDMM and SpMM passes (distributed_sparse.h:289-312) -- and scaled_out[j] (if given) receives the same number.
+template <int R, int G, int VW, int UN, bool BV, bool BO, bool SC = false>
 __global__ void __launch_bounds__(256)
 fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
                  double *__restrict__ values, int64_t rows, const double *X,
-                 const double *__restrict__ Y, double *Out) {
+                 const double *__restrict__ Y, double *Out, const double *__restrict__ scale = nullptr,
+                 double *__restrict__ scaled_out = nullptr) {
     constexpr int NV = R / (G * VW);
     static_assert(NV * G * VW == R, "R must equal NV*G*VW");
     const int lane = threadIdx.x & 31;
@@ -292,20 +295,22 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
         for (int64_t j = s; j < e; j += G) {
             const int cnt = (e - j < G) ? (int)(e - j) : G;
             int64_t mycol = 0;
-            double myval = 0.0;
+            double myval = 0.0, mysc = 1.0;
             if (gl < cnt) {
                 mycol = ld_stream_i64(col_idx + j + gl);
                 if (!BV) myval = values[j + gl];
+                if (SC) mysc = ld_stream_f64(scale + j + gl);
             }
             for (int k0 = 0; k0 < cnt; k0 += UN) {
                 double y[UN][NV][VW];
-                double vold[UN];
+                double vold[UN], vsc[UN];
 #pragma unroll
                 for (int u = 0; u < UN; u++) {
                     const int k = k0 + u;
                     const int src = k < G ? k : G - 1;
                     const int64_t c = __shfl_sync(gmask, mycol, src, G);
                     vold[u] = __shfl_sync(gmask, myval, src, G);
+                    if (SC) vsc[u] = __shfl_sync(gmask, mysc, src, G);
                     if (k < cnt) {
 #pragma unroll
                         for (int v = 0; v < NV; v++)
@@ -325,7 +330,7 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
 #pragma unroll
                         for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
                     d = group_allreduce<G>(d, gmask);
-                    const double vnew = vold[u] + d;
+                    const double vnew = SC ? (vold[u] + d) * vsc[u] : vold[u] + d;
                     if (gl == k0 + u) myval = vnew;
                     if (k0 + u < cnt) {
 #pragma unroll
@@ -336,7 +341,10 @@ fused_row_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict
                     }
                 }
             }
-            if (gl < cnt) values[j + gl] = myval;
+            if (gl < cnt) {
+                values[j + gl] = myval;
+                if (SC && scaled_out != nullptr) scaled_out[j + gl] = myval;
+            }
         }
 #pragma unroll
         for (int v = 0; v < NV; v++) st_rw<VW>(Out + row * R + (v * G + gl) * VW, acc[v]);
@@ -747,11 +755,12 @@ spmm_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restric
     }
 }
 
-template <int R, int GK, int GN, int VW, int UN, bool BV, bool BO>
+template <int R, int GK, int GN, int VW, int UN, bool BV, bool BO, bool SC = false>
 __global__ void __launch_bounds__(256)
 fused_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restrict__ col_idx,
                    double *__restrict__ values, int64_t rows, const double *X,
-                   const double *__restrict__ Y, double *Out) {
+                   const double *__restrict__ Y, double *Out, const double *__restrict__ scale = nullptr,
+                   double *__restrict__ scaled_out = nullptr) {
     constexpr int G = GK * GN;
     constexpr int NV = R / (GK * VW);
     static_assert(NV * GK * VW == R && G <= 32, "bad split shape");
@@ -774,14 +783,16 @@ fused_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restri
         }
         for (int64_t j0 = s; j0 < e; j0 += GN * UN) {
             double y[UN][NV][VW];
-            double vold[UN];
+            double vold[UN], vsc[UN];
 #pragma unroll
             for (int u = 0; u < UN; u++) {
                 const int64_t j = j0 + u * GN + np;
                 vold[u] = 0.0;
+                vsc[u] = 1.0;
                 if (j < e) {
                     const int64_t c = ld_stream_i64(col_idx + j);
                     if (!BV) vold[u] = ld_rw_f64(values + j);
+                    if (SC) vsc[u] = ld_stream_f64(scale + j);
 #pragma unroll
                     for (int v = 0; v < NV; v++)
                         ld_gather<VW>(y[u][v], Y + c * R + (v * GK + kp) * VW);
@@ -801,9 +812,12 @@ fused_split_kernel(const int64_t *__restrict__ rowStart, const int64_t *__restri
 #pragma unroll
                     for (int w = 0; w < VW; w++) d = fma(x[v][w], y[u][v][w], d);
                 d = reduce_over_k<G, GK>(d, gmask);
-                const double vnew = vold[u] + d;
+                const double vnew = SC ? (vold[u] + d) * vsc[u] : vold[u] + d;
                 if (j < e) {
-                    if (kp == 0) values[j] = vnew;
+                    if (kp == 0) {
+                        values[j] = vnew;
+                        if (SC && scaled_out != nullptr) scaled_out[j] = vnew;
+                    }
 #pragma unroll
                     for (int v = 0; v < NV; v++)
 #pragma unroll

@@ -38,6 +38,18 @@ bool device_setup_enabled(int64_t items) {
     return forced == 1 || items >= ((int64_t)1 << 18);
 }
 
+bool Runtime::managed_mode_ = [] {
+    const char *e = getenv("HNH_MANAGED_MEMORY");
+    return e != nullptr && atoi(e) != 0;
+}();
+void host_access_fence_slow() {
+    if (Runtime::get().has_device()) Runtime::get().sync_all();
+}
+int enable_host_access_mode() {
+    Runtime::set_managed_mode(true);
+    return 1;
+}
+
 Runtime &Runtime::get() {
     static Runtime r;
     return r;
@@ -94,23 +106,40 @@ void Runtime::sync_all() {
     if (copy_out_) cuda_check(cudaStreamSynchronize(copy_out_), "sync copy-out");
 }
 
+cudaEvent_t Runtime::take_event() {
+    if (!free_events_.empty()) {
+        cudaEvent_t ev = free_events_.back();
+        free_events_.pop_back();
+        return ev;
+    }
+    cudaEvent_t ev;
+    cuda_check(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate");
+    return ev;
+}
+
 void *Runtime::alloc(size_t bytes) {
     init();
     void *p = nullptr;
     const size_t b = bytes ? ((bytes + 255) & ~(size_t)255) : 256;
     auto it = cache_.find(b);
     if (it != cache_.end() && !it->second.empty()) {
-        p = it->second.back();
+        Cached c = it->second.back();
         it->second.pop_back();
-        return p;
+        for (cudaEvent_t ev : c.ev)
+            if (ev) {
+                cuda_check(cudaStreamWaitEvent(compute_, ev, 0), "cudaStreamWaitEvent");
+                free_events_.push_back(ev);
+            }
+        return c.p;
     }
-    cudaError_t e = cudaMalloc(&p, b);
+    auto raw = [&](void **q) { return managed_mode_ ? cudaMallocManaged(q, b, cudaMemAttachGlobal) : cudaMalloc(q, b); };
+    cudaError_t e = raw(&p);
     if (e == cudaErrorMemoryAllocation) {  // give cached blocks back and retry once
         cudaGetLastError();
         trim();
-        e = cudaMalloc(&p, b);
+        e = raw(&p);
     }
-    cuda_check(e, "cudaMalloc");
+    cuda_check(e, managed_mode_ ? "cudaMallocManaged" : "cudaMalloc");
     sizes_[p] = b;
     allocated_ += b;
     return p;
@@ -123,15 +152,34 @@ void Runtime::free(void *p) {
         cudaFree(p);
         return;
     }
-    cache_[it->second].push_back(p);
+    Cached c{p, {nullptr, nullptr, nullptr}};
+    if (inited_) {
+        cudaStream_t side[3] = {comm_, copy_in_, copy_out_};
+        for (int i = 0; i < 3; i++)
+            if (side[i]) {
+                cudaEvent_t ev = nullptr;
+                try {
+                    ev = take_event();
+                    cuda_check(cudaEventRecord(ev, side[i]), "cudaEventRecord");
+                    c.ev[i] = ev;
+                } catch (...) {  // free() runs in destructors: never throw; fall back to draining the stream
+                    if (ev) free_events_.push_back(ev);
+                    cudaStreamSynchronize(side[i]);
+                    cudaGetLastError();
+                }
+            }
+    }
+    cache_[it->second].push_back(c);
 }
 
 void Runtime::trim() {
     for (auto &kv : cache_)
-        for (void *p : kv.second) {
+        for (Cached &c : kv.second) {
             allocated_ -= kv.first;
-            sizes_.erase(p);
-            cudaFree(p);
+            sizes_.erase(c.p);
+            for (cudaEvent_t ev : c.ev)
+                if (ev) free_events_.push_back(ev);
+            cudaFree(c.p);
         }
     cache_.clear();
 }

@@ -89,8 +89,18 @@ size_t StandardKernel::fused_local(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B
     if (blk->transpose) throw hnh::Error(HNH_E_MODE, "fused_local needs a non-transposed block");
     CSRHandle *h = blk->getActive();
     int f = flags | (first_visit ? HNH_FLAG_BETA0_VALUES : 0) | (out_is_zero ? HNH_FLAG_BETA0_OUT : 0);
-    abi_check(hnh_fused_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords,
-                            X.data(), B.data(), Out.data(), (int)X.cols(), f, Runtime::get().compute_stream()),
+    const double *scale = nullptr;
+    double *scaled_out = nullptr;
+    if (sddmm_scale != nullptr) {  // S values folded into the fused kernel (see sparse_kernels.h)
+        const int64_t off = (int64_t)S.blockStarts[(size_t)block];
+        if (off + blk->num_coords > sddmm_scale->size() || (sddmm_scaled_out && off + blk->num_coords > sddmm_scaled_out->size()))
+            throw hnh::Error(HNH_E_INVALID, "fused_local: the S value vectors are shorter than the local sparse matrix");
+        scale = sddmm_scale->data() + off;
+        if (sddmm_scaled_out) scaled_out = sddmm_scaled_out->data() + off;
+    }
+    abi_check(hnh_fused_scaled_f64(h->rowStart.data(), h->col_idx.data(), h->values.data(), blk->rows, blk->num_coords,
+                                   X.data(), B.data(), Out.data(), (int)X.cols(), f, scale, scaled_out,
+                                   Runtime::get().compute_stream()),
               "hnh_fused_f64");
     return 0;
 }

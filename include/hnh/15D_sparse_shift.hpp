@@ -101,20 +101,7 @@ public:
         hnh::Comm &ring = *grid->col_world;
         const int steps = p / c;
 
-        if (initial_replicate && c > 1) {
-            // chunk t of every rank of the row world, side by side: all rows of R-slice i in
-            // global order (reference :203-215)
-            const int64_t cols = colside->cols();
-            accumulation_buffer.resize(colside->rows() * c, cols);
-            rt.chain(compute(), comm());
-            region_begin("Replication Time", comm());
-            const size_t chunk = (size_t)col_width * (size_t)cols;
-            for (int t = 0; t < steps; t++)
-                grid->row_world->allgather(colside->data() + chunk * t, accumulation_buffer.data() + chunk * c * t,
-                                           sizeof(double) * chunk, comm());
-            region_end("Replication Time", comm());
-            rt.chain(comm(), compute());
-        }
+        if (initial_replicate && c > 1) gather_colside(*colside, col_width);
         DenseMatrix &gathered = c > 1 ? accumulation_buffer : *colside;
 
         region_begin("Computation Time", compute());
@@ -181,7 +168,60 @@ public:
         }
     }
 
+    // FusedMM.  When the CSR block never moves (p / c == 1: every rank sees its whole row block of S and, after the
+    // all-gather, every row of the other factor at full width) the SDDMM and the SpMM of the reference's two passes
+    // (distributed_sparse.h:289-312) are ONE kernel per call: each gathered row is read once, the Hadamard product
+    // with Svalues is applied to the dot in registers, sddmm_buffer and the CSR values receive S o dots exactly as the
+    // two-pass form leaves them.  Otherwise: the reference's two passes.
+    void fusedSpMM(DenseMatrix &localA, DenseMatrix &localB, VectorXd &Svalues, VectorXd &sddmm_buffer, MatMode mode) override {
+        StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
+        const int64_t width = localA.cols();
+        const bool table_width = width >= 4 && width <= 256 && (width & (width - 1)) == 0;
+        if (sk == nullptr || p / c != 1 || !table_width || width != localB.cols() || sk->sddmm_scale != nullptr) {
+            Distributed_Sparse::fusedSpMM(localA, localB, Svalues, sddmm_buffer, mode);
+            return;
+        }
+        const bool a_mode = mode == Amat;
+        DenseMatrix &rowside = a_mode ? localA : localB, &colside = a_mode ? localB : localA;
+        SpmatLocal *choice = a_mode ? S.get() : ST.get();
+        const int64_t total = (int64_t)choice->blockStarts.back();
+        if (Svalues.size() != total)
+            throw hnh::Error(-1, "SValues has " + to_string(Svalues.size()) + " entries, the local sparse matrix " + to_string(total));
+        if (sddmm_buffer.size() != total) sddmm_buffer.resize(total);
+        if (c > 1) gather_colside(colside, a_mode ? blockBwidth : blockAwidth);
+        DenseMatrix &gathered = c > 1 ? accumulation_buffer : colside;
+        region_begin("Computation Time", compute());
+        sk->sddmm_scale = &Svalues;
+        sk->sddmm_scaled_out = &sddmm_buffer;
+        try {
+            // in place: output row i depends on input row i of the row-side factor only
+            sk->fused_local(*choice, rowside, gathered, rowside, 0, true, true);
+        } catch (...) {
+            sk->sddmm_scale = nullptr;
+            sk->sddmm_scaled_out = nullptr;
+            throw;
+        }
+        sk->sddmm_scale = nullptr;
+        sk->sddmm_scaled_out = nullptr;
+        region_end("Computation Time", compute());
+    }
+
 private:
+    // chunk t of every rank of the row world, side by side: all rows of R-slice i in global order (reference :203-215)
+    void gather_colside(DenseMatrix &colside, int col_width) {
+        hnh::Runtime &rt = hnh::Runtime::get();
+        const int64_t cols = colside.cols();
+        accumulation_buffer.resize(colside.rows() * c, cols);
+        rt.chain(compute(), comm());
+        region_begin("Replication Time", comm());
+        const size_t chunk = (size_t)col_width * (size_t)cols;
+        for (int t = 0; t < p / c; t++)
+            grid->row_world->allgather(colside.data() + chunk * t, accumulation_buffer.data() + chunk * c * t,
+                                       sizeof(double) * chunk, comm());
+        region_end("Replication Time", comm());
+        rt.chain(comm(), compute());
+    }
+
     // localise rows, exchange per-rank nnz along the ring, build the single CSR block
     vector<int> make_monolith(SpmatLocal &m, int block_height, int ncols) {
         m.mod_coordinates((uint64_t)block_height, 0);

@@ -55,11 +55,17 @@ public:
     static VectorXd Constant(int64_t n, double value);
 
     int64_t size() const { return n_; }
-    double *data() { return buf_.data(); }
-    const double *data() const { return buf_.data(); }
+    double *data() { hnh::host_access_fence(); return buf_.data(); }
+    const double *data() const { hnh::host_access_fence(); return buf_.data(); }
     void resize(int64_t n) { buf_.resize((size_t)n); n_ = n; }
     void setZero() { setConstant(0.0); }
     void setConstant(double v);
+    // Element access from the HOST (`scale_vector[i]`, als_conjugate_gradients.cpp:21): only in host-access mode
+    // (hnh::Runtime::managed_mode), where the storage is managed memory; throws otherwise.
+    double &operator[](int64_t i);
+    double operator[](int64_t i) const { return const_cast<VectorXd &>(*this)[i]; }
+    // `v.array() += c` of the reference (als_conjugate_gradients.cpp:96-97): the array view is the vector itself
+    VectorXd &array() { return *this; }
 
     VectorXd cwiseProduct(const VectorXd &o) const;
     VectorXd cwiseQuotient(const VectorXd &o) const;
@@ -123,12 +129,13 @@ public:
     int64_t rows() const { return rows_; }
     int64_t cols() const { return cols_; }
     int64_t size() const { return rows_ * cols_; }
-    double *data() { return buf_.data(); }
-    const double *data() const { return buf_.data(); }
+    double *data() { hnh::host_access_fence(); return buf_.data(); }
+    const double *data() const { hnh::host_access_fence(); return buf_.data(); }
     void resize(int64_t rows, int64_t cols);
     void setZero() { setConstant(0.0); }
     void setConstant(double v);
     void setRandom(uint64_t seed);  // uniform(-1, 1), counter-based (Eigen::setRandom)
+    void setRandom();               // the same with the next seed of a per-process sequence (Eigen's signature)
     RowBlock middleRows(int64_t start, int64_t n) {
         return RowBlock{buf_.data() + start * cols_, n, cols_};
     }
@@ -139,7 +146,19 @@ public:
     DenseMatrix &operator-=(const DenseMatrix &o);
     DenseMatrix operator+(const DenseMatrix &o) const;
     DenseMatrix operator-(const DenseMatrix &o) const;
-    DenseMatrix cwiseProduct(const DenseMatrix &o) const;
+    // `A.cwiseProduct(B)`: a lazy product, so that the reference's `A.cwiseProduct(B).rowwise().sum()`
+    // (als_conjugate_gradients.cpp:9-11) is ONE batched-dot kernel; converts to a DenseMatrix anywhere else.
+    struct CwiseProduct {
+        const DenseMatrix &a, &b;
+        operator DenseMatrix() const;
+        struct Rowwise {
+            const DenseMatrix &a, &b;
+            VectorXd sum() const;
+        };
+        Rowwise rowwise() const { return Rowwise{a, b}; }
+        double squaredNorm() const { return DenseMatrix(*this).squaredNorm(); }
+    };
+    CwiseProduct cwiseProduct(const DenseMatrix &o) const;
     double squaredNorm() const;
 
     // matrix product (gat.hpp:90 `buffers[i] * wMats[j]`): this library's DMMA GEMM (hnh_dgemm_f64) on the compute stream
@@ -172,6 +191,8 @@ private:
     hnh::DeviceBuffer<double> buf_;
     int64_t rows_ = 0, cols_ = 0;
 };
+
+DenseMatrix operator*(double s, const DenseMatrix &m);  // `lambda * A` (als_conjugate_gradients.cpp:286,298)
 
 // batch_dot_product / scale_matrix_rows of als_conjugate_gradients.cpp:9-29 on the device
 VectorXd batch_dot_product(const DenseMatrix &A, const DenseMatrix &B);

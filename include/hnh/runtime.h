@@ -41,11 +41,22 @@ public:
     void chain(cudaStream_t signaler, cudaStream_t waiter);
     void sync_all();
 
+    // Host-access (compat) mode: alloc() hands out cudaMallocManaged memory, so that code written against the
+    // reference's HOST Eigen matrices -- which takes `double *p = m.data()` and loops over p on the CPU
+    // (als_conjugate_gradients.cpp:13-26) -- runs unchanged; DenseMatrix / VectorXd::data() then drain the compute
+    // stream before handing the pointer out (host_access_fence).  Off by default: the product keeps everything in
+    // plain device memory.  Turned on by HNH_MANAGED_MEMORY=1 or by including the compat <Eigen/Dense>.  Must be chosen
+    // before the first allocation.
+    static bool managed_mode() { return managed_mode_; }
+    static void set_managed_mode(bool on) { managed_mode_ = on; }
+
     // Caching allocator: free() keeps the block on an exact-size free list and alloc() reuses
     // it, so per-call temporaries (BufferPair::extra, accumulation buffers -- which the
     // reference re-allocates on every algorithm() call, common.h:56-60,
     // 15D_dense_shift.hpp:309) cost no cudaMalloc in steady state.  Reuse is stream-ordered on
-    // compute_stream(); operations join comm_stream() back before returning.
+    // compute_stream(); free() additionally records an event on every side stream (communication, host copies) and
+    // alloc() makes the compute stream wait for them before the block is handed out again, so a block is never
+    // recycled under work that was still in flight on another stream when its owner died.
     void *alloc(size_t bytes);  // never returns null; bytes==0 -> 256-byte dummy
     void free(void *p);
     void trim();  // cudaFree everything on the free lists
@@ -56,6 +67,7 @@ public:
 private:
     Runtime() = default;
     void init();
+    static bool managed_mode_;
     bool inited_ = false;
     int dev_ = -1;
     cudaStream_t compute_ = nullptr, comm_ = nullptr, copy_in_ = nullptr, copy_out_ = nullptr;
@@ -63,7 +75,15 @@ private:
     size_t chain_next_ = 0;
     size_t allocated_ = 0;
     std::map<void *, size_t> sizes_;
-    std::map<size_t, std::vector<void *>> cache_;
+    // a cached block remembers where the side streams stood when it was freed: whoever reuses it (on the compute
+    // stream) first waits for the communication / copy work that had been enqueued by then
+    struct Cached {
+        void *p;
+        cudaEvent_t ev[3];
+    };
+    std::map<size_t, std::vector<Cached>> cache_;
+    std::vector<cudaEvent_t> free_events_;
+    cudaEvent_t take_event();
 };
 
 // Wall-clock phases of the (untimed) setup path -- tuple generation, redistribution (bucket, exchange, sort),
@@ -81,6 +101,15 @@ struct SetupPhase {  // RAII: adds its lifetime to `phase`
 // HNH_DEVICE_SETUP: "1" force the device-side setup path, "0" force the host path, unset: device when one is
 // present and the job is large enough to pay for the copies.
 bool device_setup_enabled(int64_t items);
+
+// In host-access mode: everything enqueued on the library's streams so far is complete when this returns (the pointer
+// a caller is about to dereference on the CPU is coherent).  A no-op otherwise.
+void host_access_fence_slow();
+inline void host_access_fence() {
+    if (Runtime::managed_mode()) host_access_fence_slow();
+}
+// for static initialisers of compat headers: switches host-access mode on, returns 1
+int enable_host_access_mode();
 
 // Simple owning device array.
 template <typename T>

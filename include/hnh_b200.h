@@ -108,6 +108,13 @@ int hnh_spmm_f64(const int64_t *rowStart, const int64_t *col_idx, const double *
 int hnh_fused_f64(const int64_t *rowStart, const int64_t *col_idx, double *values,
                   int64_t rows, int64_t nnz, const double *X, const double *Y, double *Out,
                   int r, int flags, void *stream);
+/* The same with the caller's S values folded in (the Hadamard product the reference applies between its SDDMM and
+ * SpMM passes, distributed_sparse.h:289-312): values[i] = scale[i] * dot, Out += sum_i values[i] * Y[col_i], and
+ * scaled_out[i] (optional) = values[i] -- the user-visible SDDMM result.  Needs HNH_FLAG_BETA0_VALUES, a table width
+ * and aligned operands (HNH_E_INVALID otherwise: use the separate calls). */
+int hnh_fused_scaled_f64(const int64_t *rowStart, const int64_t *col_idx, double *values, int64_t rows,
+                         int64_t nnz, const double *X, const double *Y, double *Out, int r, int flags,
+                         const double *scale, double *scaled_out, void *stream);
 
 /* ---- K4: value plumbing (SpmatLocal.hpp:571-605, 15D_dense_shift.hpp:366) -------------- */
 int hnh_fill_f64(double *dst, int64_t n, double value, void *stream);

@@ -105,6 +105,45 @@ def test_reference_self_check_program_runs_on_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("alg,R", [("15d_fusion2", 16), ("15d_fusion1", 16), ("15d_sparse", 8)])
+def test_reference_als_source_runs_unchanged_and_matches_the_device_als(alg, R):
+    """BASELINE.json north_star: "drops into ... als_conjugate_gradients unchanged".  als_reference_main is this repo's
+    small driver + the REFERENCE's als_conjugate_gradients.cpp compiled unchanged (Eigen expressions, the host loop
+    over data() in scale_matrix_rows, raw MPI_Allreduce: host-access mode).  One alternating round of its cg_optimizer
+    on coordinate-determined inputs must give the numbers of the library's device-resident ALS on the same inputs."""
+    import numpy as np
+    import torch
+    from distributed_sddmm_b200 import driver as D
+    from oracle import ref
+    exe = os.path.join(PKG, "als_reference_main")
+    if not os.path.exists(exe):
+        pytest.skip("als_reference_main is built only where /root/reference exists")
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    logM, npr = 9, 6
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    p = subprocess.run([exe, str(logM), str(npr), alg, str(R), "1", "10"], capture_output=True, text=True, timeout=600, env=env)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-2000:]
+    rec = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    assert rec["host_access_mode"] is True
+    # the same run through the library's own ALS (csrc/als_conjugate_gradients.cpp: all algebra in CUDA kernels)
+    D.world_init("self")
+    try:
+        N = 1 << logM
+        S = D.SpmatLocal.load_er(logM, npr)
+        a = D.Algorithm(alg, S, R, 1)
+        mats = [ref.pattern(N, R, salt) / R for salt in (1, 2, 3, 4)]
+        (before, after), A, B = D.als_run(a, *mats, 1, 10)
+        del a, S
+    finally:
+        D.world_finalize(destroy_process_group=False)
+    assert abs(rec["residual_before"] - before) <= 1e-12 * abs(before)
+    assert after < before and abs(rec["residual_after"] - after) <= 1e-9 * abs(after), (rec, before, after)
+    assert abs(rec["fingerprint_A"] - float(np.sum(A * A))) <= 1e-9 * rec["fingerprint_A"]
+    assert abs(rec["fingerprint_B"] - float(np.sum(B * B))) <= 1e-9 * rec["fingerprint_B"]
+
+
+@pytest.mark.gpu
 def test_reference_benchmark_harness_runs_on_gpu(tmp_path):
     """bench_erdos_renyi.cpp AND the reference's own benchmark_dist.cpp (benchmark_algorithm: algorithm selection,
     benchmark inputs, five-trial loop, FLOP model, JSON record), both compiled unchanged, on this library's classes.
