@@ -332,6 +332,9 @@ def sample_parity(logM, npr, R, alg, A, B, Sv, res, rank, world, shifts=False, r
                  "rows": rows_checked, "nnz": nnz_checked, "max_rel_err": err}
 
 
+_progress = lambda what: None  # noqa: E731  (set by run_native)
+
+
 def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
     """One fusedSpMM on position-dependent operands (oracle/ref.py::pattern, exactly representable) at the FULL
     benchmark size, on the data plane that was just timed (same algorithm object, same rings), checked two ways:
@@ -347,6 +350,7 @@ def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
     try:
         N, R = 1 << args.logM, args.R
         topA, leftA, nrA, ncA = (int(x) for x in alg.submatrices("A")[0])
+        _progress("parity: FusedMM on the pattern operands + row sample against the C port")
         got, out["sample"] = sample_parity(args.logM, args.nnz_per_row, R, alg, A, B, Sv, res, rank, world)
         A.fill(0.001)
         B.fill(0.001)
@@ -360,6 +364,7 @@ def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
             if world > 1:
                 dist.broadcast(flag, src=0)
             if int(flag[0]):
+                _progress("parity: the reference's fusedSpMM on the host cores (rank 0), then hand-out of its rows")
                 if rank == 0 and pattern_ref is None:
                     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
                     with _quiet_stdout():
@@ -385,6 +390,7 @@ def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
                             mine[off:off + m] = buf.numpy()
                 else:
                     mine = pattern_ref[topA:topA + live]
+                _progress("parity: comparing")
                 loc = torch.tensor([float(np.abs(got[:live] - mine).max()), float(np.abs(mine).max())], dtype=torch.float64)
                 sq = torch.tensor([float(np.sum(got[:live] ** 2)), float(np.sum(mine ** 2))], dtype=torch.float64)
                 if world > 1:
@@ -417,10 +423,21 @@ def run_native(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
+    # --share-gpu (testing aid, never a measurement): all ranks on cuda:0 over the gloo-backed External transport, to
+    # exercise the multi-rank control flow of this file on a one-GPU box
+    torch.cuda.set_device(0 if args.share_gpu else local_rank)
     L = lib()
-    rank, world = D.world_init()
+    rank, world = D.world_init("gloo" if (args.share_gpu and world > 1) else None)
     import torch.distributed as dist
+    t_start = time.perf_counter()
+
+    def progress(what):
+        """Phase marker on stderr (rank 0): a hung or slow phase of a remote run can be told from its log."""
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_start:7.1f} s] {what}", file=sys.stderr, flush=True)
+
+    global _progress
+    _progress = progress
 
     def max_over_ranks(x: float) -> float:
         if world == 1:
@@ -435,8 +452,10 @@ def run_native(args):
             L.hnhd_barrier()
 
     N, R, c = 1 << args.logM, args.R, args.c
+    progress("generating the matrix")
     S = D.SpmatLocal.load_er(args.logM, args.nnz_per_row, SEED)
     nnz = S.info()["dist_nnz"]
+    progress("building the algorithm object (redistribution, CSR blocks)")
     alg = D.Algorithm(args.alg, S, R, c)
     info = alg.info()
     A, B = alg.like_A_matrix(0.001), alg.like_B_matrix(0.001)
@@ -446,6 +465,7 @@ def run_native(args):
     def step():
         alg.fusedSpMM(A, B, Sv, res, "A")
 
+    progress(f"warm-up ({args.warmup}) and timed loop ({args.steps})")
     for _ in range(args.warmup):
         step()
     sync_barrier()
@@ -478,10 +498,14 @@ def run_native(args):
                 "kernel": ("fused_row_kernel" if args.alg == "15d_fusion2" else "sddmm_row_kernel + spmm_row_kernel") +
                           f"<{R}>, {steps_ring} launch(es) per step per GPU",
                 "kernel_ms_per_step": comp_ms, "algorithmic_bytes_per_step_per_gpu": bytes_rank}
-    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(prof) and world == 1:
+    # DRAM bytes per launch of this kernel from the committed ncu capture of the same command (a profiler cannot run
+    # inside the timed region); only for the exact configuration that was captured
+    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(prof) and world == 1 and (args.logM, args.nnz_per_row) == (20, 32):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{'fused' if args.alg == '15d_fusion2' else 'spmm'}_{R}")
+            tj = json.load(open(prof))
+            roofline["traffic"] = tj.get(f"{'fused' if args.alg == '15d_fusion2' else 'spmm'}_{R}")
+            roofline["traffic_source"] = "profiles/r02_traffic.json (ncu --set full, same kernel and config)"
         except Exception:  # noqa: BLE001
             pass
     shift_ms = perf.get("Cyclic Shift Time", 0.0) * 1e3 / args.steps
@@ -503,7 +527,29 @@ def run_native(args):
         other = {oname: {"ms_per_step": oms, "gflops": flops / (oms * 1e-3) / 1e9}}
         del oalg, oSv, ores
 
+    progress("timed loop done")
+    # ---- the north-star transport, for the record: the same ring as grouped NCCL send/recv (HNH_RING=nccl) ----
+    if world > 1 and not args.no_other:
+        try:
+            os.environ["HNH_RING"] = "nccl"
+            nalg = D.Algorithm(args.alg, S, R, c)
+            nSv, nres = nalg.like_S_values(1.0), nalg.like_S_values(0.0)
+            for _ in range(2):
+                nalg.fusedSpMM(A, B, nSv, nres, "A")
+            sync_barrier()
+            D.timer_start()
+            for _ in range(5):
+                nalg.fusedSpMM(A, B, nSv, nres, "A")
+            nms = max_over_ranks(D.timer_stop()) / 5
+            sync_barrier()
+            other = dict(other or {}, nccl_send_recv_ring={"ms_per_step": nms, "gflops": flops / (nms * 1e-3) / 1e9,
+                                                          "ring": nalg.info().get("ring")})
+            del nalg, nSv, nres
+        finally:
+            os.environ.pop("HNH_RING", None)
+
     # ---- e2e: per-rank pinned HOST buffers in, result out, copies inside the timed region ----
+    progress("e2e leg (host operands)")
     shapeA, shapeB = A.shape, B.shape
     hA = torch.full(shapeA, 0.001, dtype=torch.float64).pin_memory()
     hB = torch.full(shapeB, 0.001, dtype=torch.float64).pin_memory()
@@ -539,6 +585,7 @@ def run_native(args):
     cpu = None
     pattern_ref = None
     want_full = args.parity == "full"
+    progress("cpu baseline / parity leg")
     if world == 1 and not args.no_cpu_baseline:
         g, cores, kind, desc, _, _, pattern_ref = cpu_reference_fusedmm(args, 1, 3, want_pattern=want_full)
         cpu = {"value": g, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": desc}
@@ -557,6 +604,8 @@ def run_native(args):
         except Exception:  # noqa: BLE001
             nvlink = None
 
+    ring_info = alg.info().get("ring")  # collective (per-rank nnz are gathered): every rank must make this call
+    progress("done")
     if rank == 0:
         line = {
             "metric": METRIC, "value": gflops, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -565,7 +614,7 @@ def run_native(args):
             "config": workload_config(args),
             "run": {"where": "cuda", "p": world, "c": c, "nnz": nnz, "ring_steps": steps_ring,
                     "local_rows": alg.dims.localArows, "transport": info.get("transport"),
-                    "ring": alg.info().get("ring"),
+                    "ring": ring_info,
                     "collectives": ("NCCL all-gather / reduce-scatter over row_world" if c > 1 else "none")},
             "hbm_gbs_achieved_per_gpu": bytes_rank / (ms * 1e-3) / 1e9,
             "roofline": roofline,
@@ -599,6 +648,7 @@ def main():
     ap.add_argument("--e2e-plain", action="store_true",
                     help="e2e leg as copy_from_host(A), (B); fusedSpMM; copy_to_host instead of the default "
                          "Distributed_Sparse::fusedSpMM_host (upload / kernels / download pipelined)")
+    ap.add_argument("--share-gpu", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--parity", default="full", choices=["full", "sample", "off"],
                     help="correctness leg after the timed loops (never timed): 'sample' = a row sample per rank against the "
                          "C port of the reference kernels; 'full' = that plus every output row against one fusedSpMM of "
