@@ -297,39 +297,46 @@ def sample_parity(logM, npr, R, alg, A, B, Sv, res, rank, world, shifts=False, r
     if shifts:
         alg.de_shift(A, B, "sddmmA")
     got = A.to_host()
-    flat = got.reshape(-1)
-    err, rows_checked, nnz_checked, at = 0.0, 0, 0, 0
-    for top, left, nr, nc in subsA:
-        top, left, nr, nc = int(top), int(left), int(nr), int(nc)
-        blk = flat[at:at + nr * nc].reshape(nr, nc)
-        at += nr * nc
-        live = max(0, min(nr, N - top))
-        n_s = min(live, rows_per_block)
-        if n_s == 0:
-            continue
-        lo = top + (live - n_s) // 3
-        cap = n_s * npr
-        r_, c_, v_ = np.empty(cap, np.uint64), np.empty(cap, np.uint64), np.empty(cap, np.float64)
-        n = L.hnh_er_generate_host(logM, npr, SEED, lo, lo + n_s, r_.ctypes.data, c_.ctypes.data, v_.ctypes.data, cap)
-        r_, c_, v_ = r_[:n], c_[:n], v_[:n]
-        ucols, inv = np.unique(c_, return_inverse=True)
-        csr = orc.coo_to_csr(n_s, len(ucols), r_ - np.uint64(lo), inv.astype(np.uint64), v_)
-        want = np.zeros((n_s, R))
-        orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), ref.pattern(n_s, R, 1, row0=lo),
-                        ref.pattern_rows(ucols, R, 2), want)
-        want = want[:, left:left + nc]
-        have = blk[lo - top:lo - top + n_s]
-        err = max(err, float(np.abs(have - want).max() / max(float(np.abs(want).max()), 1e-300)))
-        rows_checked += n_s
-        nnz_checked += int(n)
+    err, rows_checked, nnz_checked, local_error = 0.0, 0, 0, None
+    try:  # a failure of the checker on one rank must not leave the others waiting in the reductions below
+        flat, at = got.reshape(-1), 0
+        for top, left, nr, nc in subsA:
+            top, left, nr, nc = int(top), int(left), int(nr), int(nc)
+            blk = flat[at:at + nr * nc].reshape(nr, nc)
+            at += nr * nc
+            live = max(0, min(nr, N - top))
+            n_s = min(live, rows_per_block)
+            if n_s == 0:
+                continue
+            lo = top + (live - n_s) // 3
+            cap = n_s * npr
+            r_, c_, v_ = np.empty(cap, np.uint64), np.empty(cap, np.uint64), np.empty(cap, np.float64)
+            n = L.hnh_er_generate_host(logM, npr, SEED, lo, lo + n_s, r_.ctypes.data, c_.ctypes.data, v_.ctypes.data, cap)
+            r_, c_, v_ = r_[:n], c_[:n], v_[:n]
+            ucols, inv = np.unique(c_, return_inverse=True)
+            csr = orc.coo_to_csr(n_s, len(ucols), r_ - np.uint64(lo), inv.astype(np.uint64), v_)
+            want = np.zeros((n_s, R))
+            orc.fused_block(csr.rowStart, csr.row_idx, csr.col_idx, np.zeros(csr.nnz), ref.pattern(n_s, R, 1, row0=lo),
+                            ref.pattern_rows(ucols, R, 2), want)
+            want = want[:, left:left + nc]
+            have = blk[lo - top:lo - top + n_s]
+            err = max(err, float(np.abs(have - want).max() / max(float(np.abs(want).max()), 1e-300)))
+            rows_checked += n_s
+            nnz_checked += int(n)
+
+    except Exception as e:  # noqa: BLE001
+        local_error, err = f"{type(e).__name__}: {e}", float("inf")
     stats = torch.tensor([err, float(rows_checked), float(nnz_checked)], dtype=torch.float64)
     if world > 1:
         worst, tot = stats.clone(), stats.clone()
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         err, rows_checked, nnz_checked = float(worst[0]), int(tot[1]), int(tot[2])
-    return got, {"checker": "oracle/hnh_oracle.c (C port of sparse_kernels.cpp:44-55 + CSR SpMM), same tuples",
-                 "rows": rows_checked, "nnz": nnz_checked, "max_rel_err": err}
+    rec = {"checker": "oracle/hnh_oracle.c (C port of sparse_kernels.cpp:44-55 + CSR SpMM), same tuples",
+           "rows": rows_checked, "nnz": nnz_checked, "max_rel_err": err}
+    if local_error:
+        rec["error_on_this_rank"] = local_error
+    return got, rec
 
 
 _progress = lambda what: None  # noqa: E731  (set by run_native)
@@ -359,16 +366,24 @@ def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
 
         # ---- full: the reference's own fusedSpMM ----
         if want_full:
-            flag = torch.tensor([1 if (rank != 0 or pattern_ref is not None or
-                                       (ref.available() and hasattr(ref.lib(), "ref_time_fused_check"))) else 0])
-            if world > 1:
-                dist.broadcast(flag, src=0)
-            if int(flag[0]):
-                _progress("parity: the reference's fusedSpMM on the host cores (rank 0), then hand-out of its rows")
-                if rank == 0 and pattern_ref is None:
+            # rank 0 computes the reference first; only then do the ranks agree (one broadcast) on whether there is
+            # anything to compare with -- a failure of the CPU run cannot strand the others in a collective
+            ref_error = None
+            if rank == 0 and pattern_ref is None:
+                _progress("parity: the reference's fusedSpMM on the host cores (rank 0)")
+                try:
+                    if not (ref.available() and hasattr(ref.lib(), "ref_time_fused_check")):
+                        raise RuntimeError("oracle/_ref is not built")
                     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
                     with _quiet_stdout():
                         _, _, pattern_ref = ref.time_fused_check(args.alg, 1, R, args.logM, args.nnz_per_row, SEED, 0, 0, cores)
+                except Exception as e:  # noqa: BLE001
+                    ref_error, pattern_ref = f"{type(e).__name__}: {e}", None
+            flag = torch.tensor([1 if (rank == 0 and pattern_ref is not None) else 0])
+            if world > 1:
+                dist.broadcast(flag, src=0)
+            if int(flag[0]):
+                _progress("parity: handing the reference rows to the ranks")
                 if world > 1:  # hand every rank its rows (gloo send/recv, 64 MiB pieces)
                     where = [None] * world
                     dist.all_gather_object(where, (int(topA), int(live)))
@@ -401,6 +416,8 @@ def parity_check(args, alg, A, B, Sv, res, rank, world, pattern_ref, want_full):
                                "fingerprint_squared_norm": {"native": float(sq[0]), "reference": float(sq[1])}}
             else:
                 out["full"] = None
+                if ref_error:
+                    out["full_skipped"] = ref_error
         errs = [out["sample"]["max_rel_err"]] + ([out["full"]["max_rel_err"]] if out.get("full") else [])
         out["max_rel_err"] = max(errs)
         out["n"] = (N if out.get("full") else rows_s)
