@@ -515,6 +515,12 @@ def run_native(args):
                 "kernel": ("fused_row_kernel" if args.alg == "15d_fusion2" else "sddmm_row_kernel + spmm_row_kernel") +
                           f"<{R}>, {steps_ring} launch(es) per step per GPU",
                 "kernel_ms_per_step": comp_ms, "algorithmic_bytes_per_step_per_gpu": bytes_rank}
+    # The per-block launches of a multi-rank step re-read the row-side factor and read + write the accumulator once
+    # per ring step; `frac` counts those bytes (they are what the launched kernels must move).  The share of ONE launch
+    # over all of the rank's nonzeros -- what a perfectly fused step would move -- is reported beside it.
+    minimal = nnz_rank * (R * 8 + 8 + 8) + (rows_stationary + 1) * 8 + 2 * rows_stationary * R * 8
+    roofline["minimal_bytes_per_step_per_gpu"] = minimal
+    roofline["frac_on_minimal_bytes"] = (minimal / (comp_ms * 1e-3) / 1e9 / peak) if comp_ms > 0 else 0.0
     # DRAM bytes per launch of this kernel from the committed ncu capture of the same command (a profiler cannot run
     # inside the timed region); only for the exact configuration that was captured
     prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
@@ -617,7 +623,9 @@ def run_native(args):
         try:  # explanatory only: never let it cost the line
             nb = nvlink_bytes_per_rank(args.alg, world, c, alg.dims.localBrows, R)
             nvlink = {"bytes_in_per_gpu_per_step": nb, "peak_gbs": NVLINK_GBS_NOMINAL, "peak_kind": "nominal",
-                      "bound_ms": nb / (NVLINK_GBS_NOMINAL * 1e9) * 1e3, "achieved_gbs": nb / (ms * 1e-3) / 1e9}
+                      "bound_ms": nb / (NVLINK_GBS_NOMINAL * 1e9) * 1e3, "achieved_gbs": nb / (ms * 1e-3) / 1e9,
+                      # every pushed shard is read once here and written once at the neighbour by the copy engines
+                      "copy_engine_hbm_bytes_per_gpu_per_step": 2.0 * nb}
         except Exception:  # noqa: BLE001
             nvlink = None
 
