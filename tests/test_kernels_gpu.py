@@ -272,6 +272,65 @@ def test_beta0_overwrite_variants(hnh, R):
                                  dA.data_ptr(), dA.data_ptr(), R, BETA0, gu.stream()) == -1
 
 
+@pytest.mark.parametrize("R", [4, 32, 128, 256, 12])
+def test_scaled_epilogues_match_oracle(hnh, R):
+    """hnh_sddmm_scaled_f64 / hnh_fused_scaled_f64: the Hadamard product with the caller's S values folded into the
+    kernel (reference: a separate `SValues.cwiseProduct(getCSRValues())` pass, 15D_dense_shift.hpp:364-368).  Must equal
+    kernel-then-multiply exactly (one rounding of the product either way); R = 12 takes the generic fallback."""
+    N, rows, cols, vals, A, B, rng = make_problem(10, 8, R, seed=13)
+    csr = orc.coo_to_csr(N, N, rows, cols, vals)
+    scale = rng.uniform(0.5, 1.5, csr.nnz)
+    rs, ci = gu.dev(csr.rowStart), gu.dev(csr.col_idx)
+    dA, dB, dS = gu.dev(A), gu.dev(B), gu.dev(scale)
+    st = gu.stream()
+    dots = gu.run_sddmm(csr, A, B, flags=4)
+    BETA0, SCALE_VALUES, BETA0_VALUES, BETA0_OUT = 4, 256, 16, 32
+
+    def sddmm(flags, with_out, v0=None):
+        v = gu.dev(np.zeros(csr.nnz) if v0 is None else v0)
+        out = torch.full((csr.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        rc = hnh.hnh_sddmm_scaled_f64(rs.data_ptr(), ci.data_ptr(), v.data_ptr(), N, csr.nnz, dA.data_ptr(), dB.data_ptr(), R,
+                                      flags, dS.data_ptr(), out.data_ptr() if with_out else None, st)
+        assert rc == 0, hnh.hnh_last_error_string()
+        torch.cuda.synchronize()
+        return v.cpu().numpy(), out.cpu().numpy()
+
+    v, out = sddmm(BETA0, True)              # values = dot, scaled_out = scale * dot
+    assert np.array_equal(v, dots) and np.array_equal(out, scale * dots)
+    v, out = sddmm(BETA0 | SCALE_VALUES, True)   # both receive the product
+    assert np.array_equal(v, scale * dots) and np.array_equal(out, scale * dots)
+    v, _ = sddmm(BETA0, False)               # no second output: the product replaces the values
+    assert np.array_equal(v, scale * dots)
+    v0 = rng.uniform(-1, 1, csr.nnz)         # accumulate form: old value added before scaling
+    acc = gu.run_sddmm(csr, A, B, v0)
+    v, out = sddmm(0, True, v0)
+    assert np.array_equal(v, acc) and np.array_equal(out, scale * acc)
+
+    if R == 12:  # no scaled fused kernel outside the dispatch table: the call must say so
+        vz = gu.dev(np.zeros(csr.nnz)); o = gu.dev(np.zeros((N, R)))
+        assert hnh.hnh_fused_scaled_f64(rs.data_ptr(), ci.data_ptr(), vz.data_ptr(), N, csr.nnz, dA.data_ptr(), dB.data_ptr(),
+                                        o.data_ptr(), R, BETA0_VALUES, dS.data_ptr(), None, st) == -1
+        return
+    # fused: values = scale * dot, Out (+)= sum values * Y, scaled_out = values -- against SDDMM, multiply, SpMM
+    want_vals = scale * dots
+    O0 = rng.uniform(-1, 1, (N, R))
+    want_out = gu.run_spmm(csr, want_vals, B, O0)
+    for bo in (0, BETA0_OUT):
+        vz, o = gu.dev(np.zeros(csr.nnz)), gu.dev(O0)
+        so = torch.full((csr.nnz,), float("nan"), dtype=torch.float64, device="cuda")
+        rc = hnh.hnh_fused_scaled_f64(rs.data_ptr(), ci.data_ptr(), vz.data_ptr(), N, csr.nnz, dA.data_ptr(), dB.data_ptr(),
+                                      o.data_ptr(), R, BETA0_VALUES | bo, dS.data_ptr(), so.data_ptr(), st)
+        assert rc == 0, hnh.hnh_last_error_string()
+        torch.cuda.synchronize()
+        assert np.array_equal(vz.cpu().numpy(), want_vals) and np.array_equal(so.cpu().numpy(), want_vals)
+        ref_out = want_out if bo == 0 else gu.run_spmm(csr, want_vals, B, np.zeros((N, R)))
+        assert rel_err(o.cpu().numpy(), ref_out) < RTOL
+    # needs the first-visit form
+    vz, o = gu.dev(np.zeros(csr.nnz)), gu.dev(O0)
+    assert hnh.hnh_fused_scaled_f64(rs.data_ptr(), ci.data_ptr(), vz.data_ptr(), N, csr.nnz, dA.data_ptr(), dB.data_ptr(),
+                                    o.data_ptr(), R, 0, dS.data_ptr(), None, st) == -1
+
+
 @pytest.mark.parametrize("R", [128, 256])
 def test_tma_staged_variants_match_oracle(hnh, R):
     """HNH_FLAG_TMA_STAGE: the X tile arrives by cp.async.bulk + mbarrier; results must be identical in
