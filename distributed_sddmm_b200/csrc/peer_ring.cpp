@@ -118,6 +118,9 @@ void PeerRing::connect(const std::vector<std::array<void *, 2>> &local, int resi
     std::memset(&mine, 0, sizeof mine);
     bool ok = true;
     try {
+        // fault injection for the tests: the named ring rank fails here, as a rank without peer access would
+        if (const char *e = getenv("HNH_TEST_PEERRING_FAIL"))
+            if (atoi(e) == me) throw Error(HNH_E_CUDA, "injected failure (HNH_TEST_PEERRING_FAIL)");
         load_driver();
         int dev = 0;
         cuda_check(cudaGetDevice(&dev), "cudaGetDevice");

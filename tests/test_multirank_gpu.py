@@ -245,3 +245,19 @@ def test_device_side_setup_matches_reference(nproc):
             raise AssertionError(f"case {c['name']} (p={nproc}, device setup, reference from {src}): {e}") from e
         checked += 1
     assert checked > 0
+
+
+def test_peer_ring_failure_on_one_rank_is_a_collective_fallback():
+    """A rank that cannot map its neighbours' buffers (injected: HNH_TEST_PEERRING_FAIL) must not leave the others in the
+    ring's barrier: every rank releases what it acquired and all take the transport's send/recv path together -- same
+    results, and the algorithm reports which ring it really used."""
+    cases = [U.case("15d_fusion2", 1, 8, 7, 5), U.case("15d_sparse", 1, 8, 7, 5), U.case("15d_fusion1", 1, 8, 7, 5)]
+    got = U.run_cases(2, cases, transport_for(2), timeout=600, env_extra={"HNH_TEST_PEERRING_FAIL": "1"})
+    for c in cases:
+        want, src = U.reference_for(c, 2)
+        if want is None:
+            pytest.skip("neither oracle/_ref nor golden files available")
+        U.compare_layout(got[c["name"]], want, c["alg"])
+        U.compare_ops(got[c["name"]], want, c["script"])
+        for rank_out in got[c["name"]]:
+            assert json.loads(str(rank_out["info"]))["ring"] == "send/recv of the transport", c["name"]
