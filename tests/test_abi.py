@@ -46,6 +46,27 @@ def test_argument_validation_needs_no_gpu(hnh):
     assert hnh.hnh_spmm_f64(None, None, None, 0, 0, None, None, 8, 0, None) == 0
 
 
+def test_round2_entry_points_validate_without_a_gpu(hnh):
+    """The scaled-epilogue kernels and the device tuple pipeline reject bad arguments before touching the device."""
+    assert hnh.hnh_sddmm_scaled_f64(None, None, None, 4, -1, None, None, 8, 0, None, None, None) == -1
+    # scaled_out without scale
+    buf = (C.c_double * 8)()
+    assert hnh.hnh_sddmm_scaled_f64(None, None, None, 4, 4, None, None, 8, 0, None, buf, None) == -1
+    assert b"scaled_out without scale" in hnh.hnh_last_error_string()
+    assert hnh.hnh_fused_scaled_f64(None, None, None, 4, 4, None, None, None, 8, 0, None, buf, None) == -1
+    # empty block: successful no-op
+    assert hnh.hnh_sddmm_scaled_f64(None, None, None, 4, 0, None, None, 8, 0, None, None, None) == 0
+    starts = (C.c_int64 * 3)()
+    assert hnh.hnh_tuples_bucket_by_owner_device(None, None, None, -1, 0, 1, 1, None, 1, 1, 2, None, None, None, starts, None) == -1
+    assert hnh.hnh_tuples_sort_colmajor_device(None, None, None, -1, 1, 1, None) == -1
+    assert hnh.hnh_tuples_sort_colmajor_device(None, None, None, 1, 1, 1, None) == 0      # nothing to sort
+    assert hnh.hnh_tuples_mod_device(None, None, 0, 3, 3, None) == 0
+    assert hnh.hnh_tuples_block_starts_device(None, 5, 0, 2, starts, None) == -1           # zero block width
+    assert hnh.hnh_tuples_block_starts_device(None, 0, 4, 2, starts, None) == 0 and list(starts) == [0, 0, 0]
+    assert hnh.hnh_dgemm_f64(None, None, None, -1, 1, 1, None) == -1
+    assert hnh.hnh_dgemm_f64(None, None, None, 0, 4, 4, None) == 0
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_LIB", None)
     monkeypatch.setattr(_lib, "library_path", lambda: str(tmp_path / "nope.so"))
