@@ -56,30 +56,25 @@ size_t StandardKernel::spmm_local(SpmatLocal &S, DenseMatrix &A, DenseMatrix &B,
 
 void StandardKernel::fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block,
                                       int64_t row0, int64_t nrows, bool out_is_zero) {
-    const int64_t r = X.cols();
-    fused_rows_at(S, X.data() + row0 * r, B, Out.data() + row0 * r, r, block, row0, nrows, out_is_zero);
-}
-
-void StandardKernel::fused_rows_at(SpmatLocal &S, const double *x_rows, DenseMatrix &B, double *out_rows, int64_t r, int block,
-                                   int64_t row0, int64_t nrows, bool out_is_zero) {
     CSRLocal *blk = S.csr_blocks[block];
     if (nrows <= 0) return;
+    const int64_t r = X.cols();
     if (blk == nullptr || blk->num_coords == 0) {
         if (out_is_zero)
-            hnh::cuda_check(cudaMemsetAsync(out_rows, 0, sizeof(double) * (size_t)(nrows * r), Runtime::get().compute_stream()),
-                            "cudaMemsetAsync");
+            hnh::cuda_check(cudaMemsetAsync(Out.data() + row0 * r, 0, sizeof(double) * (size_t)(nrows * r),
+                                            Runtime::get().compute_stream()), "cudaMemsetAsync");
         return;
     }
     if (blk->transpose) throw hnh::Error(HNH_E_MODE, "fused_local_rows needs a non-transposed block");
-    if (r != B.cols()) throw hnh::Error(HNH_E_INVALID, "fused_local_rows: factor widths differ");
     if (r < 4 || r > 256 || (r & (r - 1)) != 0)  // the generic kernel's overwrite mode clears the whole block's values
         throw hnh::Error(HNH_E_INVALID, "fused_local_rows: width outside the dispatch table");
     if (row0 < 0 || row0 + nrows > blk->rows) throw hnh::Error(HNH_E_INVALID, "fused_local_rows: row range");
     CSRHandle *h = blk->getActive();
-    // rowStart entries are absolute offsets into col_idx / values, so a row range is the same call on a shifted
-    // rowStart and on the first row of the operand / output windows
-    abi_check(hnh_fused_f64(h->rowStart.data() + row0, h->col_idx.data(), h->values.data(), nrows, blk->num_coords, x_rows, B.data(),
-                            out_rows, (int)r, flags | HNH_FLAG_BETA0_VALUES | (out_is_zero ? HNH_FLAG_BETA0_OUT : 0),
+    // rowStart entries are absolute offsets into col_idx / values, so a row range is the same call on shifted
+    // rowStart / X / Out pointers
+    abi_check(hnh_fused_f64(h->rowStart.data() + row0, h->col_idx.data(), h->values.data(), nrows, blk->num_coords,
+                            X.data() + row0 * r, B.data(), Out.data() + row0 * r, (int)r,
+                            flags | HNH_FLAG_BETA0_VALUES | (out_is_zero ? HNH_FLAG_BETA0_OUT : 0),
                             Runtime::get().compute_stream()),
               "hnh_fused_f64");
 }

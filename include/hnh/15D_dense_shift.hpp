@@ -18,7 +18,6 @@
 #include <memory>
 
 #include "hnh/distributed_sparse.h"
-#include "hnh_b200.h"
 
 class ShardedBlockCyclicColumn : public NonzeroDistribution {
 public:
@@ -197,9 +196,6 @@ public:
         StandardKernel *sk = dynamic_cast<StandardKernel *>(kernel);
         const int steps = p / c;
 
-        if (c == 2 && sk && overlap && overlapped_replication() && in_place_width(stationary->cols()) &&
-            fusedSpMM_pairwise(*stationary, *riding, *choice, *sk))
-            return;
         if (c > 1) replicate(*stationary, broadcast_buffer);
         DenseMatrix &gathered = c > 1 ? broadcast_buffer : *stationary;
         // With one ring step and no replication the output row i depends only on input row i:
@@ -282,89 +278,8 @@ public:
         hnh::cuda_check(cudaStreamSynchronize(out), "fusedSpMM_host");
     }
 
-    // HNH_OVERLAP_REPLICATION=1: the c = 2 FusedMM below instead of all-gather -> ring -> reduce-scatter (opt-in:
-    // parity-checked on the GPU, not yet timed on 8 GPUs)
-    static bool overlapped_replication() {
-        static const bool on = [] {
-            const char *e = getenv("HNH_OVERLAP_REPLICATION");
-            return e != nullptr && atoi(e) != 0;
-        }();
-        return on;
-    }
-
 private:
     static bool in_place_width(int64_t r) { return r >= 4 && r <= 256 && (r & (r - 1)) == 0; }
-
-    // Local kernel fusion with c = 2 and the replication hidden behind the kernels (reference: Allgather, ring,
-    // Reduce_scatter strictly one after the other, 15D_dense_shift.hpp:191-197,238-244).  The two ranks of a row world
-    // exchange over a copy-engine ring of size two (slot 0: the partner's stationary shard = the all-gather; slot 1:
-    // the partner's partial sums for MY rows = the reduce-scatter), and the rows of the 2 x localArows block row are
-    // worked in two segments so that nothing waits for a transfer that is not needed yet:
-    //   step 0      : own rows first (their operand is local) while the partner's shard flies in, then the partner's rows;
-    //   last step   : the partner's rows first -- their partial sums leave at once -- then the own rows;
-    //   afterwards  : result = own partial sums + the partner's (a + b: the same bits on both sides of the exchange).
-    // Every (segment, block) pair is one fused kernel on a row range; values and sums are those of the plain path.
-    // Returns false (nothing done) when the peer ring is not available: the caller takes the NCCL path.
-    bool fusedSpMM_pairwise(DenseMatrix &stationary, DenseMatrix &riding, SpmatLocal &choice, StandardKernel &sk) {
-        hnh::Runtime &rt = hnh::Runtime::get();
-        const int64_t rows = stationary.rows(), r = stationary.cols();
-        const size_t bytes = sizeof(double) * (size_t)(rows * r);
-        hnh::PeerRing *pair = peer_ring(grid->row_world, bytes);
-        if (pair == nullptr) return false;
-        const int steps = p / c, mine = grid->rankInRow, theirs = 1 - mine;
-        cudaStream_t side = rt.copy_in_stream();
-        pair_own_.resize(rows, r);
-        pair_theirs_.resize(rows, r);
-
-        // all-gather half: my shard into the partner's slot 0
-        rt.chain(compute(), side);
-        region_begin("Replication Time", side);
-        pair->push(0, stationary.data(), bytes, side);
-        region_end("Replication Time", side);
-
-        bool have_theirs = false;
-        auto segment = [&](bool own, int step, DenseMatrix &shard) {
-            if (!own && !have_theirs) {  // first use of the partner's shard
-                pair->expect_arrival(0);
-                pair->wait_arrival(0, compute());
-                have_theirs = true;
-            }
-            const double *x = own ? stationary.data() : (const double *)pair->slot(0);
-            double *out = own ? pair_own_.data() : pair_theirs_.data();
-            sk.fused_rows_at(choice, x, shard, out, r, block_at(step), (int64_t)(own ? mine : theirs) * rows, rows, step == 0);
-        };
-        auto send_partials = [&] {  // reduce-scatter half: the partner's rows are complete
-            rt.chain(compute(), side);
-            region_begin("Replication Time", side);
-            pair->push(1, pair_theirs_.data(), bytes, side);
-            pair->release(0, side);  // ... and its shard has been read for the last time
-            region_end("Replication Time", side);
-        };
-        ring_dense(riding, grid->col_world, true, "Cyclic Shift Time", "Computation Time", [&](int step, DenseMatrix &shard) {
-            if (step == steps - 1 && step > 0) {
-                segment(false, step, shard);
-                send_partials();
-                segment(true, step, shard);
-            } else {
-                segment(true, step, shard);
-                segment(false, step, shard);
-                if (steps == 1) send_partials();
-            }
-        });
-
-        pair->expect_arrival(1);
-        pair->wait_arrival(1, compute());
-        region_begin("Computation Time", compute());
-        hnh::abi_check(hnh_axpby_f64(stationary.data(), 1.0, pair_own_.data(), 1.0, (const double *)pair->slot(1), rows * r, compute()),
-                       "pairwise reduce");
-        region_end("Computation Time", compute());
-        rt.chain(compute(), side);
-        pair->release(1, side);
-        rt.chain(side, compute());  // later users of these buffers are ordered behind the side stream
-        return true;
-    }
-    DenseMatrix pair_own_, pair_theirs_;  // partial sums of the two row segments (fusedSpMM_pairwise)
-
     // state of a fusion-1 FusedMM in flight (see fusedSpMM)
     bool fused_pass_ = false, spmm_values_resident_ = false, riding_output_is_zero_ = false;
 

@@ -83,8 +83,4 @@ public:
     // of the dispatch table (4..256, powers of two); throws otherwise.
     void fused_local_rows(SpmatLocal &S, DenseMatrix &X, DenseMatrix &B, DenseMatrix &Out, int block, int64_t row0,
                           int64_t nrows, bool out_is_zero = true);
-    // the same with the operand / output windows given by pointer: x_rows and out_rows are row `row0` of the row-side
-    // factor and of the output (r doubles per row) -- they may live in different buffers, e.g. a peer-ring slot
-    void fused_rows_at(SpmatLocal &S, const double *x_rows, DenseMatrix &B, double *out_rows, int64_t r, int block, int64_t row0,
-                       int64_t nrows, bool out_is_zero);
 };

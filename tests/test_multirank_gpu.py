@@ -261,33 +261,3 @@ def test_peer_ring_failure_on_one_rank_is_a_collective_fallback():
         U.compare_ops(got[c["name"]], want, c["script"])
         for rank_out in got[c["name"]]:
             assert json.loads(str(rank_out["info"]))["ring"] == "send/recv of the transport", c["name"]
-
-
-PAIRWISE_CASES = {
-    2: [U.case("15d_fusion2", 2, 8, 7, 5, script=["fusedA", "fusedB", "spmmA", "fusedA"], name="pairwise_p2_r8"),
-        U.case("15d_fusion2", 2, 128, 9, 6, script=["fusedA", "fusedB"], name="nogolden_pairwise_p2_r128")],
-    4: [U.case("15d_fusion2", 2, 8, 7, 5, script=["fusedA", "fusedB", "sddmmA", "fusedA"], name="pairwise_p4_r8"),
-        U.case("15d_fusion2", 2, 8, 7, 5, n=99, script=["fusedA", "fusedB"], name="nogolden_pairwise_p4_n99")],
-}
-
-
-@pytest.mark.parametrize("nproc", [2, 4])
-def test_overlapped_replication_c2_matches_reference(nproc):
-    """HNH_OVERLAP_REPLICATION=1: the c = 2 FusedMM whose all-gather and reduce-scatter are copy-engine exchanges between
-    the two ranks of a row world, hidden behind row-segment kernels (15D_dense_shift.hpp::fusedSpMM_pairwise), against
-    the reference's Allgather -> ring -> Reduce_scatter, rank by rank; repeated calls reuse the exchange slots."""
-    from oracle import ref
-    if not ref.available():
-        pytest.skip("oracle/_ref is not built")
-    cases = PAIRWISE_CASES[nproc]
-    got = U.run_cases(nproc, cases, transport_for(nproc), timeout=900, env_extra={"HNH_OVERLAP_REPLICATION": "1"})
-    for c in cases:
-        want, src = U.reference_for(c, nproc)
-        try:
-            U.compare_layout(got[c["name"]], want, c["alg"])
-            U.compare_ops(got[c["name"]], want, c["script"])
-        except AssertionError as e:
-            raise AssertionError(f"case {c['name']} (p={nproc}, overlapped replication, reference from {src}): {e}") from e
-        # the pairwise exchange ring exists next to the column ring (p = 4) / on its own (p = 2: no column ring)
-        rings = json.loads(str(got[c["name"]][0]["info"]))["peer_rings"]
-        assert rings == (1 if nproc == 2 else 2), (c["name"], rings)
