@@ -4,7 +4,9 @@ factor, world size (2, 4, 8 gloo ranks), matrix shape (square / rectangular / si
 width; every rank's layout descriptors and CSR blocks must be bit-identical with the reference's.
     python scripts/fuzz_setup_parity.py [seed [batches]]
 Round 1: seeds 7, 11, 21-24 -> 76 configurations, 0 mismatches (one reported difference was the rowStart leftover of the
-reference's dummy entry in an EMPTY block, which nothing reads; tests/mp_util.py::compare_layout documents it)."""
+reference's dummy entry in an EMPTY block, which nothing reads; tests/mp_util.py::compare_layout documents it).
+Round 2 (after the tuple accessors / device-setup refactor of SpmatLocal): seeds 60, 61, 62 -> 132 configurations, 0
+mismatches (host path; the device path is compared with the same reference in tests/test_multirank_gpu.py)."""
 import os
 import random
 import sys
